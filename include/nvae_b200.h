@@ -1,0 +1,245 @@
+/*
+ * nvae_b200.h -- C ABI of libnvae_b200.so: B200 (sm_100a) kernels for the NVAE-TF hot path.
+ *
+ * This is the drop-in boundary.  Every entry point is an asynchronous,
+ * launch-only wrapper on the caller's CUDA stream: plain device pointers and sizes, POD
+ * descriptor structs, no C++/torch/TensorFlow types.  The caller (the TF custom-op
+ * `Compute()` bodies in tf_op/, or ctypes in nvae_tf_b200/_lib.py) owns every buffer
+ * including workspaces; kernels never allocate, never retain pointers past return and never
+ * synchronise the host.  Return value: 0 on success, a positive cudaError_t, or a negative
+ * NVAE_E_* code.  There is no CPU fallback: an unsupported shape is an error.
+ *
+ * All tensors are float32; activations NHWC, conv kernels HWIO ([R,S,Cin,Cout]), depthwise
+ * kernels [5,5,C,1], dense kernels [in,out] -- TensorFlow's layouts, so the reference's
+ * checkpoints and variables map 1:1.  "Replaces" lines cite the reference call sites
+ * (file:line in stevensdavid/nvae-tf) whose TensorFlow ops the entry point stands in for.
+ */
+#ifndef NVAE_B200_H_
+#define NVAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* nvae_stream_t;
+
+#if defined(__GNUC__)
+#define NVAE_API __attribute__((visibility("default")))
+#else
+#define NVAE_API
+#endif
+
+enum {
+  NVAE_OK = 0,
+  NVAE_E_BADSHAPE = -1,
+  NVAE_E_UNSUPPORTED = -2,
+  NVAE_E_WORKSPACE = -3,
+  NVAE_E_NULLPTR = -4,
+  NVAE_E_DRIVER = -5
+};
+
+enum { NVAE_ACT_NONE = 0, NVAE_ACT_SWISH = 1, NVAE_ACT_ELU = 2 };
+
+/* Arithmetic of the convolution GEMMs. FP32 = CUDA-core FFMA (exact-fp32 parity mode);
+ * TF32 = tcgen05 kind::tf32 on operands rounded to nearest-even TF32 by their producers;
+ * TF32X3 = 3-pass split (hi*hi + hi*lo + lo*hi), ~fp32 accuracy on the tensor cores. */
+enum { NVAE_PREC_FP32 = 0, NVAE_PREC_TF32 = 1, NVAE_PREC_TF32X3 = 2 };
+
+/* Library / device identification. Returns 100 for sm_100; build id string is static. */
+NVAE_API int nvae_version(void);
+NVAE_API const char* nvae_build_info(void);
+
+/* ------------------------------------------------------------------------------------------
+ * BatchNormalization(momentum=0.05, epsilon=1e-5)      Replaces: common.py:148,166;
+ * encoder.py:91,95,102,104; decoder.py:125,129,131,135,139-145; preprocess.py:87;
+ * postprocess.py:71,84,107 (cuDNN FusedBatchNormV3 + Eigen swish/ELU in the reference).
+ *
+ * stat is a [4][C] float block the later kernels consume: mean, invstd, scale=gamma*invstd,
+ * shift=beta-mean*scale.  training!=0: batch statistics over rows (=N*H*W), biased variance;
+ * moving_mean/var updated in place (Bessel-corrected variance, retain factor `momentum`).
+ * training==0: stat is derived from the moving statistics and x is not read.
+ * ------------------------------------------------------------------------------------------ */
+NVAE_API size_t nvae_bn_ws_bytes(int64_t rows, int C);
+NVAE_API int nvae_bn_stats(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
+                  float* moving_mean, float* moving_var, int training, float momentum, float eps,
+                  float* stat, void* ws, size_t ws_bytes, nvae_stream_t stream);
+
+/* out = act(x*scale+shift) (stat==NULL: out = act(x)); optional nearest x2 upsample
+ * (tf.image.resize "nearest", common.py:168-172: pass up_h=H, up_w=W of x, else 0,0);
+ * round_tf32!=0 rounds the result to TF32 (RN) so tcgen05 kind::tf32 consumes it exactly.
+ * lo!=NULL additionally stores the TF32-rounded residual out_full-out for the 3-pass mode. */
+NVAE_API int nvae_bn_act_fwd(const float* x, int64_t rows, int C, const float* stat, int act, int up_h, int up_w,
+                    int round_tf32, float* out, float* lo, nvae_stream_t stream);
+
+/* Backward of nvae_bn_act_fwd (+ batch-norm backward when stat!=NULL):
+ *   g = dout*act'(u)  (summed over the 2x2 replicas when upsampled)
+ *   training: dx = scale*(g - mean(g) - xhat*mean(g*xhat));  inference: dx = scale*g
+ *   dgamma = sum g*xhat, dbeta = sum g   (written with '=' unless NULL)
+ *   dx (+)= res_scale*dres when dres!=NULL;  accumulate!=0 adds into existing dx. */
+NVAE_API int nvae_bn_act_bwd(const float* dout, const float* x, int64_t rows, int C, const float* stat, int act, int up_h,
+                    int up_w, int training, const float* dres, float res_scale, int accumulate, float* dx,
+                    float* dgamma, float* dbeta, void* ws, size_t ws_bytes, nvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SqueezeExcitation + residual merge.   Replaces: common.py:129-142 fused with the cell
+ * tails encoder.py:107, decoder.py:147 (y = 0.1*x + SE(t)) and preprocess.py:107,
+ * postprocess.py:58 (y = skip + 0.1*SE(t)):   y = alpha*xres + beta*t*gate[b,c].
+ * An optional per-channel affine (stat, e.g. decoder.py:145 batch_norm4 -> se) is applied to
+ * t first: t' = t*scale+shift.  pooled/hidden/gate are saved for backward.
+ * ------------------------------------------------------------------------------------------ */
+NVAE_API int nvae_se_fwd(const float* t, const float* stat, const float* xres, int B, int HW, int C, int hid,
+                const float* w1, const float* b1, const float* w2, const float* b2, float alpha, float beta,
+                float* pooled, float* hidden, float* gate, float* y, nvae_stream_t stream);
+NVAE_API size_t nvae_se_bwd_ws_bytes(int B, int C, int hid);
+/* dt is the gradient w.r.t. t' (post-affine); dxres (+)= alpha*dy. */
+NVAE_API int nvae_se_bwd(const float* dy, const float* t, const float* stat, int B, int HW, int C, int hid, const float* w1,
+                const float* w2, const float* pooled, const float* hidden, const float* gate, float alpha,
+                float beta, float* dt, float* dxres, int dxres_accumulate, float* dw1, float* db1, float* dw2,
+                float* db2, void* ws, size_t ws_bytes, nvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DepthwiseConv2D((5,5), padding="same") with the BN-apply + swish of its input fused into
+ * the load.   Replaces: decoder.py:130,141-142 (TF DepthwiseConv2dGPUKernelNHWC + 2 more ops).
+ * ------------------------------------------------------------------------------------------ */
+NVAE_API int nvae_dwconv5x5_fwd(const float* x, const float* stat, int act, int N, int H, int W, int C, const float* w,
+                       const float* bias, float* y, nvae_stream_t stream);
+/* da = gradient w.r.t. the ACTIVATED input (feed to nvae_bn_act_bwd). */
+NVAE_API int nvae_dwconv5x5_bwd_data(const float* dy, int N, int H, int W, int C, const float* w, float* da,
+                            nvae_stream_t stream);
+NVAE_API size_t nvae_dwconv5x5_bwd_filter_ws_bytes(int N, int H, int W, int C);
+NVAE_API int nvae_dwconv5x5_bwd_filter(const float* x, const float* stat, int act, const float* dy, int N, int H, int W,
+                              int C, float* dw, float* dbias, void* ws, size_t ws_bytes, nvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-group latent math.   Replaces: Sampler.call common.py:76-102, softclamp5 util.py:49-50,
+ * Sampler.sample common.py:65-68 (epsilon supplied by the caller), the per-element KL and its
+ * row sum models.py:197-201, and (optional) calculate_log_p util.py:39-46 / decoder.py:69-71,
+ * 84-102.  enc_p/dec_p are the raw conv outputs [B,HW,2L] (mu | log_sigma halves);
+ * dec_p==NULL is the z_idx==0 branch (standard-normal prior).
+ * ------------------------------------------------------------------------------------------ */
+/* dist (nullable): [4][B,HW,L] = enc_mu, enc_sigma, dec_mu, dec_sigma (DistributionParams, common.py:12-17).
+ * log_q/log_p (nullable, both or neither) are ACCUMULATED into (+=), as decoder.py:97-102 sums over groups. */
+NVAE_API int nvae_latent_fwd(const float* enc_p, const float* dec_p, const float* eps, int B, int HW, int L, float* z,
+                    float* kl, float* log_q, float* log_p, float* dist, nvae_stream_t stream);
+/* kl_weight points at ONE device float: d(total loss)/d(kl[b]) for this group (beta*coeff_g/B). */
+NVAE_API int nvae_latent_bwd(const float* enc_p, const float* dec_p, const float* eps, const float* dz,
+                    const float* kl_weight, int B, int HW, int L, float* d_enc_p, float* d_dec_p,
+                    nvae_stream_t stream);
+
+/* KL balancing + loss assembly.   Replaces: models.py:121-126, 204-222.
+ * kl_all [G,B]; recon [B] (nullable); hyper = device floats {beta, ...} (see nvae_schedule_step).
+ * balancing: 1/0 = models.py:204 `if balancing`, -1 = decide on device as train_step does (beta<1).
+ * Outputs: kl_weight[G] = beta*c_g/B (nullable; consumed by nvae_latent_bwd), kl_loss[B] =
+ * beta*sum_g c_g*kl[g,b], scalars (nullable) [0]=total loss incl. bn_loss, [1]=mean(recon+kl_loss). */
+NVAE_API int nvae_loss_assemble(const float* kl_all, const float* recon, const float* bn_loss, const float* alphas,
+                       const float* hyper, int balancing, int G, int B, float* kl_weight, float* kl_loss,
+                       float* scalars, nvae_stream_t stream);
+
+/* Bernoulli(logits).log_prob(x) summed over H,W,C.   Replaces: models.py:242-250
+ * (tfp.distributions.Bernoulli).  logits [B,H,W,Cl] with Cl==C or Cl==1 (broadcast);
+ * crop>0 evaluates [crop:H-crop, crop:W-crop] only (models.py:243-245). */
+NVAE_API int nvae_bernoulli_ll_fwd(const float* logits, const float* x, int B, int H, int W, int C, int Cl, int crop,
+                          float* recon, nvae_stream_t stream);
+NVAE_API int nvae_bernoulli_ll_bwd(const float* logits, const float* x, int B, int H, int W, int C, int Cl, float scale,
+                          float* dlogits, nvae_stream_t stream);
+
+/* BN-gamma infinity-norm regulariser.   Replaces: models.py:252-267 (88 x (abs,max) launches).
+ * gamma k lives at params+offsets[k] with sizes[k] elements (device tables). */
+NVAE_API int nvae_bn_loss_fwd(const float* params, const int64_t* offsets, const int32_t* sizes, int n, float sr_lambda,
+                     float* loss, nvae_stream_t stream);
+/* grads+offsets[k] += sr_lambda*sign(gamma)/n_ties at the arg-max entries (tf.reduce_max gradient). */
+NVAE_API int nvae_bn_loss_bwd(const float* params, float* grads, const int64_t* offsets, const int32_t* sizes, int n,
+                     float sr_lambda, nvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * tfa.layers.SpectralNormalization(power_iterations=1), all layers in three launches, plus
+ * the packing of the conv weights into the layouts the tensor-core kernels consume.
+ * Replaces: every SpectralNormalization( call site (common.py:41,57,152,156; encoder.py:12,
+ * 61,92,96; decoder.py:110,126,132; preprocess.py:20,46-63,91; postprocess.py:29,78,96).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t w_off;    /* kernel [rows,cout] (HWIO flattened) in `params`            */
+  int64_t u_off;    /* u [cout] in `state`                                         */
+  int64_t v_off;    /* scratch v_raw [rows] in `ws` (floats)                       */
+  int64_t t_off;    /* scratch partial t [n_chunks,cout] in `ws` (floats)          */
+  int64_t rnd_off;  /* TF32-rounded HWIO copy in `pack` (floats) or -1             */
+  int64_t tr_off;   /* TF32-rounded transposed copy [cout_pad][taps][cin_pad] or -1 */
+  int32_t rows, cout, taps, cin, cin_pad, cout_pad;
+  int32_t chunk0;   /* first row-chunk index of this layer in the flat chunk list  */
+  int32_t n_chunks;
+} NvaeSnLayer;
+#define NVAE_SN_ROWS_PER_CHUNK 64
+/* power_iter!=0: v=l2n(W u), u'=l2n(v W), sigma=(vW).u', W/=sigma, u=u' (in place);
+ * power_iter==0: weights left untouched (inference / SN inactive), only (re)packed. */
+NVAE_API int nvae_spectral_norm(float* params, float* state, float* pack, const NvaeSnLayer* layers_dev, int n_layers,
+                       const int32_t* chunk_layer_dev, int n_chunks_total, int power_iter, int pack_lo,
+                       float* sigma_out, float* ws, nvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Conv2D(padding="same").   Replaces: every layers.Conv2D call listed under K1 of SURVEY 2.1
+ * (cuDNN fwd / bwd-data / bwd-filter in the reference) incl. tf.concat decoder.py:115
+ * (second source x2) and the residual add of encoder.py:16.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t N, H, W, Cin;   /* input tensor x [N,H,W,Cin]                                 */
+  int32_t Cin2;           /* channels of the concatenated second source x2 (0 = none)   */
+  int32_t Cout, R, S;     /* kernel HWIO [R,S,Cin+Cin2,Cout]                            */
+  int32_t stride;         /* 1 or 2 (both dims)                                          */
+  int32_t Ho, Wo;         /* output spatial size = ceil(H/stride)                        */
+  int32_t pad_t, pad_l;   /* TF SAME padding before (extra padding goes after)           */
+  int32_t precision;      /* NVAE_PREC_*                                                 */
+  int32_t y_ld, y_off;    /* y / dy / residual are [N,Ho,Wo,y_ld] and this conv owns channels
+                             [y_off, y_off+Cout) (tf.concat of preprocess.py:73); y_ld==0: Cout */
+  float pre_scale, pre_shift; /* x' = x*pre_scale+pre_shift applied on load (preprocess.py:39) FP32 path only */
+} NvaeConvDesc;
+
+NVAE_API size_t nvae_conv2d_ws_bytes(const NvaeConvDesc* d, int which /*0 fwd,1 dgrad,2 wgrad*/);
+/* y = conv(x ++ x2, w) + bias (+ residual).  w: HWIO fp32 master; w_tr: packed transposed TF32
+ * copy from nvae_spectral_norm (tensor-core path; may be NULL for NVAE_PREC_FP32). */
+NVAE_API int nvae_conv2d_fwd(const NvaeConvDesc* d, const float* x, const float* x2, const float* w, const float* w_tr,
+                    const float* bias, const float* residual, float* y, void* ws, size_t ws_bytes,
+                    nvae_stream_t stream);
+/* dx (+)= dgrad(dy, w) for the first Cin channels, dx2 for the concatenated Cin2 channels. */
+NVAE_API int nvae_conv2d_dgrad(const NvaeConvDesc* d, const float* dy, const float* w, const float* w_rnd, float* dx,
+                      float* dx2, int accumulate, void* ws, size_t ws_bytes, nvae_stream_t stream);
+/* dw = wgrad(x ++ x2, dy) (HWIO, '='), dbias = column sums of dy (NULL to skip). */
+NVAE_API int nvae_conv2d_wgrad(const NvaeConvDesc* d, const float* x, const float* x2, const float* dy, float* dw,
+                      float* dbias, void* ws, size_t ws_bytes, nvae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer + schedules.   Replaces: optimizers.Adamax + CosineDecay train.py:128-131,
+ * models.py:121-122,128-129.  `counters` (device int64[2]) = {warm-up metric (model.steps or .epoch),
+ * optimizer iterations}; hyper (device float[8]) = {beta, lr_t = lr/(1-b1^t), lr, t, metric}, computed
+ * from the counters BEFORE they advance (advance bit0: ++metric, bit1: ++iterations).  One launch
+ * per step, graph-capturable.
+ * ------------------------------------------------------------------------------------------ */
+NVAE_API int nvae_schedule_step(int64_t* counters, float* hyper, float warmup_iters /*0.3*n_total*/, float lr0,
+                       float decay_steps, float b1, int advance, nvae_stream_t stream);
+NVAE_API int nvae_adamax(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float b1, float b2,
+                float eps, float grad_scale, nvae_stream_t stream);
+
+/* Small utilities used by the host mirror (all launch-only). */
+NVAE_API int nvae_fill(float* p, int64_t n, float value, nvae_stream_t stream);
+NVAE_API int nvae_axpby(const float* x, float a, float* y, float b, int64_t n, nvae_stream_t stream); /* y=a*x+b*y */
+NVAE_API int nvae_broadcast_rows(const float* src, int64_t row_elems, int B, float* dst, nvae_stream_t stream);
+NVAE_API int nvae_reduce_rows(const float* src, int64_t row_elems, int B, float* dst, nvae_stream_t stream);
+/* z = mu + eps*(sigma*sigma_scale): Sampler.sample on materialised parameters (common.py:65-68;
+ * models.py:140-145 temperature, :175-176 extra draws). */
+NVAE_API int nvae_reparam(const float* mu, const float* sigma, const float* eps, float sigma_scale, float* z, int64_t n,
+                 nvae_stream_t stream);
+/* Philox4x32-10 standard normals (production epsilon for common.py:67; parity runs inject eps). */
+NVAE_API int nvae_philox_normal(float* out, int64_t n, uint64_t seed, const int64_t* counters, uint64_t stream_id,
+                       nvae_stream_t stream);
+/* Bernoulli(logits) images: mode 0 = probs_parameter()/mean() = sigmoid(l); mode 1 = sample().
+ * Replaces: models.py:168-174, 185-188. */
+NVAE_API int nvae_bernoulli_image(const float* logits, int64_t n, int mode, uint64_t seed, uint64_t stream_id, float* out,
+                         nvae_stream_t stream);
+NVAE_API int nvae_l2_flush(float* scratch, int64_t n, nvae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVAE_B200_H_ */

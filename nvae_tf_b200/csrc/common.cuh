@@ -1,0 +1,93 @@
+// Shared device helpers for libnvae_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nvae_b200.h"
+
+#define NVAE_RETURN_IF_LAUNCH_FAILED()                 \
+  do {                                                 \
+    cudaError_t e__ = cudaGetLastError();              \
+    if (e__ != cudaSuccess) return (int)e__;           \
+  } while (0)
+
+#define NVAE_CUDA_TRY(expr)                            \
+  do {                                                 \
+    cudaError_t e__ = (expr);                          \
+    if (e__ != cudaSuccess) return (int)e__;           \
+  } while (0)
+
+namespace nvae {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ---- activations -------------------------------------------------------------
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float u) {
+  if (ACT == NVAE_ACT_SWISH) return u / (1.f + expf(-u));
+  if (ACT == NVAE_ACT_ELU) return u > 0.f ? u : expm1f(u);
+  return u;
+}
+template <int ACT>
+__device__ __forceinline__ float act_grad(float u) {
+  if (ACT == NVAE_ACT_SWISH) {
+    float s = 1.f / (1.f + expf(-u));
+    return s * (1.f + u * (1.f - s));
+  }
+  if (ACT == NVAE_ACT_ELU) return u > 0.f ? 1.f : expf(u);
+  return 1.f;
+}
+__device__ __forceinline__ float act_fwd_rt(float u, int act) {
+  return act == NVAE_ACT_SWISH ? act_fwd<NVAE_ACT_SWISH>(u) : act == NVAE_ACT_ELU ? act_fwd<NVAE_ACT_ELU>(u) : u;
+}
+__device__ __forceinline__ float act_grad_rt(float u, int act) {
+  return act == NVAE_ACT_SWISH ? act_grad<NVAE_ACT_SWISH>(u) : act == NVAE_ACT_ELU ? act_grad<NVAE_ACT_ELU>(u) : 1.f;
+}
+
+// round-to-nearest TF32 (10-bit mantissa); low 13 bits of the result are zero
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---- warp / block reductions ----------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Deterministic block sum (fixed tree); result valid in every thread. `red` needs 33 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// ---- 128-bit streaming access -----------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stg4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+}  // namespace nvae

@@ -1,0 +1,237 @@
+// Depthwise 5x5 convolution (decoder.py:130) fwd / bwd-data / bwd-filter.  CUDA-core, HBM-bound:
+// each CTA stages a zero-haloed [imgs][H+4][W+4..][32ch] tile in shared memory (128-byte channel
+// rows -> fully coalesced 128-bit global loads, conflict-free LDS.128), with the BatchNorm-apply +
+// swish of decoder.py:141 fused into the staging so the activated tensor never exists in HBM.
+#include "common.cuh"
+
+namespace nvae {
+
+constexpr int kDwThreads = 256;
+constexpr int kDwCC = 32;  // channels per CTA (8 float4 lanes)
+constexpr int kDwTW = 4;   // outputs per thread along W
+
+struct DwGeom {
+  int WQ, PW, PH, imgs, ngroups, nchunks;
+  size_t smem_tile;  // floats
+};
+
+static DwGeom dw_geom(int N, int H, int W, int C) {
+  DwGeom g;
+  g.WQ = (W + kDwTW - 1) / kDwTW;
+  g.PW = g.WQ * kDwTW + 4;
+  g.PH = H + 4;
+  const int items_per_img = 8 * H * g.WQ;
+  int imgs = (2 * kDwThreads + items_per_img - 1) / items_per_img;  // ~512 work items per CTA
+  if (imgs < 1) imgs = 1;
+  if (imgs > N) imgs = N;
+  while (imgs > 1 && (size_t)imgs * g.PH * g.PW * kDwCC * sizeof(float) > 96 * 1024) --imgs;
+  g.imgs = imgs;
+  g.ngroups = (N + imgs - 1) / imgs;
+  g.nchunks = C / kDwCC;
+  g.smem_tile = (size_t)imgs * g.PH * g.PW * kDwCC;
+  return g;
+}
+
+// Stage `imgs` images of the channel chunk into the haloed tile, applying act(x*scale+shift).
+template <bool PROLOGUE>
+__device__ __forceinline__ void dw_stage(float* tile, const float* __restrict__ x, const float* __restrict__ stat,
+                                         int act, int n0, int nimg, int H, int W, int C, int c0, int PH, int PW) {
+  const int c4 = threadIdx.x & 7;
+  float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0);
+  if (PROLOGUE && stat != nullptr) {
+    sc = ldg4(stat + 2 * C + c0 + c4 * 4);
+    sh = ldg4(stat + 3 * C + c0 + c4 * 4);
+  }
+  const int total = nimg * PH * PW;
+  for (int p = threadIdx.x >> 3; p < total; p += kDwThreads >> 3) {
+    const int pw = p % PW, t = p / PW, ph = t % PH, im = t / PH;
+    const int h = ph - 2, w = pw - 2;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      v = ldg4(x + (((int64_t)(n0 + im) * H + h) * W + w) * C + c0 + c4 * 4);
+      if (PROLOGUE) {
+        v.x = act_fwd_rt(fmaf(v.x, sc.x, sh.x), act); v.y = act_fwd_rt(fmaf(v.y, sc.y, sh.y), act);
+        v.z = act_fwd_rt(fmaf(v.z, sc.z, sh.z), act); v.w = act_fwd_rt(fmaf(v.w, sc.w, sh.w), act);
+      }
+    }
+    *reinterpret_cast<float4*>(tile + (size_t)p * kDwCC + c4 * 4) = v;
+  }
+}
+
+// FLIP=false: y = dwconv(act(bn(x))) + bias.   FLIP=true: da = dwconv_transpose(dy) (no prologue, no bias)
+template <bool FLIP>
+__global__ void __launch_bounds__(kDwThreads) dwconv5x5_kernel(const float* __restrict__ x,
+                                                               const float* __restrict__ stat, int act, int N, int H,
+                                                               int W, int C, const float* __restrict__ wts,
+                                                               const float* __restrict__ bias, float* __restrict__ y,
+                                                               int imgs, int WQ, int PH, int PW) {
+  extern __shared__ __align__(16) float smem[];
+  float* wsm = smem;             // [25][32]
+  float* tile = smem + 25 * kDwCC;
+  const int c0 = blockIdx.x * kDwCC, n0 = blockIdx.y * imgs;
+  const int nimg = (N - n0) < imgs ? (N - n0) : imgs;
+  for (int i = threadIdx.x; i < 25 * kDwCC; i += kDwThreads) {
+    const int tap = i / kDwCC, c = i % kDwCC;
+    wsm[i] = __ldg(wts + (int64_t)(FLIP ? 24 - tap : tap) * C + c0 + c);
+  }
+  dw_stage<!FLIP>(tile, x, stat, act, n0, nimg, H, W, C, c0, PH, PW);
+  __syncthreads();
+  const int c4 = threadIdx.x & 7;
+  float4 bv = make_float4(0, 0, 0, 0);
+  if (!FLIP && bias != nullptr) bv = ldg4(bias + c0 + c4 * 4);
+  const int items = nimg * H * WQ;
+  for (int it = threadIdx.x >> 3; it < items; it += kDwThreads >> 3) {
+    const int wq = it % WQ, t = it / WQ, h = t % H, im = t / H;
+    const int w0 = wq * kDwTW;
+    float4 acc[kDwTW];
+#pragma unroll
+    for (int j = 0; j < kDwTW; ++j) acc[j] = bv;
+    const float* trow = tile + ((size_t)(im * PH + h) * PW + w0) * kDwCC + c4 * 4;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      float4 win[kDwTW + 4];
+#pragma unroll
+      for (int j = 0; j < kDwTW + 4; ++j)
+        win[j] = *reinterpret_cast<const float4*>(trow + ((size_t)r * PW + j) * kDwCC);
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        const float4 wv = *reinterpret_cast<const float4*>(wsm + (r * 5 + s) * kDwCC + c4 * 4);
+#pragma unroll
+        for (int j = 0; j < kDwTW; ++j) {
+          acc[j].x = fmaf(win[j + s].x, wv.x, acc[j].x); acc[j].y = fmaf(win[j + s].y, wv.y, acc[j].y);
+          acc[j].z = fmaf(win[j + s].z, wv.z, acc[j].z); acc[j].w = fmaf(win[j + s].w, wv.w, acc[j].w);
+        }
+      }
+    }
+    float* yo = y + (((int64_t)(n0 + im) * H + h) * W + w0) * C + c0 + c4 * 4;
+#pragma unroll
+    for (int j = 0; j < kDwTW; ++j)
+      if (w0 + j < W) stg4(yo + (int64_t)j * C, acc[j]);
+  }
+}
+
+// partial[g][26][C]: taps 0..24 = sum a*dy, 25 = sum dy (bias gradient)
+__global__ void __launch_bounds__(kDwThreads) dwconv5x5_bwd_filter_kernel(
+    const float* __restrict__ x, const float* __restrict__ stat, int act, const float* __restrict__ dy, int N, int H,
+    int W, int C, float* __restrict__ partial, int imgs, int PH, int PW) {
+  extern __shared__ __align__(16) float smem[];
+  float* tile = smem;                                  // haloed activated input
+  float* dtile = smem + (size_t)imgs * PH * PW * kDwCC;  // [imgs][H][W][32] dy
+  const int c0 = blockIdx.x * kDwCC, n0 = blockIdx.y * imgs;
+  const int nimg = (N - n0) < imgs ? (N - n0) : imgs;
+  dw_stage<true>(tile, x, stat, act, n0, nimg, H, W, C, c0, PH, PW);
+  const int c4 = threadIdx.x & 7;
+  const int npix = nimg * H * W;
+  for (int p = threadIdx.x >> 3; p < npix; p += kDwThreads >> 3)
+    *reinterpret_cast<float4*>(dtile + (size_t)p * kDwCC + c4 * 4) =
+        ldg4(dy + ((int64_t)n0 * H * W + p) * C + c0 + c4 * 4);
+  __syncthreads();
+  const int tap = threadIdx.x >> 3;  // 0..31; 25 = bias, >25 idle
+  if (tap > 25) return;
+  float4 acc = make_float4(0, 0, 0, 0);
+  if (tap == 25) {
+    for (int p = 0; p < npix; ++p) {
+      const float4 d = *reinterpret_cast<const float4*>(dtile + (size_t)p * kDwCC + c4 * 4);
+      acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+    }
+  } else {
+    const int r = tap / 5, s = tap % 5;
+    for (int im = 0; im < nimg; ++im)
+      for (int h = 0; h < H; ++h) {
+        const float* ar = tile + ((size_t)(im * PH + h + r) * PW + s) * kDwCC + c4 * 4;
+        const float* dr = dtile + ((size_t)(im * H + h) * W) * kDwCC + c4 * 4;
+#pragma unroll 4
+        for (int w = 0; w < W; ++w) {
+          const float4 a = *reinterpret_cast<const float4*>(ar + (size_t)w * kDwCC);
+          const float4 d = *reinterpret_cast<const float4*>(dr + (size_t)w * kDwCC);
+          acc.x = fmaf(a.x, d.x, acc.x); acc.y = fmaf(a.y, d.y, acc.y);
+          acc.z = fmaf(a.z, d.z, acc.z); acc.w = fmaf(a.w, d.w, acc.w);
+        }
+      }
+  }
+  stg4(partial + ((int64_t)blockIdx.y * 26 + tap) * C + c0 + c4 * 4, acc);
+}
+
+__global__ void dwconv5x5_bwd_filter_reduce_kernel(const float* __restrict__ partial, int ngroups, int C,
+                                                   float* __restrict__ dw, float* __restrict__ dbias) {
+  const int total = 26 * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int g = 0; g < ngroups; ++g) s += partial[(int64_t)g * total + i];
+    if (i < 25 * C) dw[i] = s;
+    else if (dbias != nullptr) dbias[i - 25 * C] = s;
+  }
+}
+
+static int dw_check(int N, int H, int W, int C) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % kDwCC)) return NVAE_E_BADSHAPE;
+  DwGeom g = dw_geom(N, H, W, C);
+  if ((g.smem_tile * 2 + 25 * kDwCC) * sizeof(float) > 200 * 1024) return NVAE_E_UNSUPPORTED;
+  return NVAE_OK;
+}
+
+}  // namespace nvae
+
+using namespace nvae;
+
+template <bool FLIP>
+static int dw_launch(const float* x, const float* stat, int act, int N, int H, int W, int C, const float* w,
+                     const float* bias, float* y, cudaStream_t stream) {
+  DwGeom g = dw_geom(N, H, W, C);
+  const size_t smem = (g.smem_tile + 25 * kDwCC) * sizeof(float);
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[FLIP]) {
+    NVAE_CUDA_TRY(cudaFuncSetAttribute(dwconv5x5_kernel<FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured[FLIP] = 200 * 1024;
+  }
+  dwconv5x5_kernel<FLIP><<<dim3(g.nchunks, g.ngroups), kDwThreads, smem, stream>>>(x, stat, act, N, H, W, C, w, bias, y,
+                                                                                   g.imgs, g.WQ, g.PH, g.PW);
+  NVAE_RETURN_IF_LAUNCH_FAILED();
+  return NVAE_OK;
+}
+
+extern "C" int nvae_dwconv5x5_fwd(const float* x, const float* stat, int act, int N, int H, int W, int C,
+                                  const float* w, const float* bias, float* y, nvae_stream_t stream) {
+  int rc = dw_check(N, H, W, C);
+  if (rc) return rc;
+  if (!x || !w || !y) return NVAE_E_NULLPTR;
+  return dw_launch<false>(x, stat, act, N, H, W, C, w, bias, y, stream);
+}
+
+extern "C" int nvae_dwconv5x5_bwd_data(const float* dy, int N, int H, int W, int C, const float* w, float* da,
+                                       nvae_stream_t stream) {
+  int rc = dw_check(N, H, W, C);
+  if (rc) return rc;
+  if (!dy || !w || !da) return NVAE_E_NULLPTR;
+  return dw_launch<true>(dy, nullptr, NVAE_ACT_NONE, N, H, W, C, w, nullptr, da, stream);
+}
+
+extern "C" size_t nvae_dwconv5x5_bwd_filter_ws_bytes(int N, int H, int W, int C) {
+  if (dw_check(N, H, W, C)) return 0;
+  DwGeom g = dw_geom(N, H, W, C);
+  return (size_t)g.ngroups * 26 * C * sizeof(float);
+}
+
+extern "C" int nvae_dwconv5x5_bwd_filter(const float* x, const float* stat, int act, const float* dy, int N, int H,
+                                         int W, int C, float* dw, float* dbias, void* ws, size_t ws_bytes,
+                                         nvae_stream_t stream) {
+  int rc = dw_check(N, H, W, C);
+  if (rc) return rc;
+  if (!x || !dy || !dw) return NVAE_E_NULLPTR;
+  DwGeom g = dw_geom(N, H, W, C);
+  if (ws == nullptr || ws_bytes < (size_t)g.ngroups * 26 * C * sizeof(float)) return NVAE_E_WORKSPACE;
+  const size_t smem = (g.smem_tile + (size_t)g.imgs * H * W * kDwCC) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    NVAE_CUDA_TRY(cudaFuncSetAttribute(dwconv5x5_bwd_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024));
+    configured = true;
+  }
+  float* partial = reinterpret_cast<float*>(ws);
+  dwconv5x5_bwd_filter_kernel<<<dim3(g.nchunks, g.ngroups), kDwThreads, smem, stream>>>(x, stat, act, dy, N, H, W, C,
+                                                                                        partial, g.imgs, g.PH, g.PW);
+  NVAE_RETURN_IF_LAUNCH_FAILED();
+  dwconv5x5_bwd_filter_reduce_kernel<<<(26 * C + 255) / 256, 256, 0, stream>>>(partial, g.ngroups, C, dw, dbias);
+  NVAE_RETURN_IF_LAUNCH_FAILED();
+  return NVAE_OK;
+}
