@@ -278,8 +278,9 @@ class Runtime:
             return e
         out = self.empty(*shape)
         cnt = getattr(self, "counters", None)
-        self.lib.philox_normal(out.data_ptr(), out.numel(), self.philox_seed, cnt.data_ptr() if cnt is not None else None,
-                               self.eps_i, self.stream)
+        # device-side iteration counter (counters[1]) keys the stream so graph replays draw fresh noise
+        self.lib.philox_normal(out.data_ptr(), out.numel(), self.philox_seed,
+                               cnt[1:].data_ptr() if cnt is not None else None, self.eps_i, self.stream)
         self.eps_i += 1
         return out
 

@@ -1,0 +1,264 @@
+"""GPU parity of the residual cells and of the whole NVAE step (forward, losses, every gradient,
+optimizer update, moving statistics) against the float64 oracle and the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import nvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL_ACT = 1e-3   # BASELINE north star: per-tensor max relative error on activations and gradients
+TOL_LOSS = 1e-3  # ELBO / KL terms within 0.1 %
+FP32_TOL = 1e-4  # what the fp32 CUDA-core arithmetic mode actually achieves (checked too)
+
+
+def npy(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def f32(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+def _load_params(rt, rng, jitter=0.3):
+    p = {}
+    for v in rt.variables.values():
+        if "variance" in v.name:
+            a = rng.uniform(0.5, 1.5, v.shape)
+        elif v.name.endswith("gamma"):
+            a = rng.normal(1, 0.2, v.shape)
+        elif v.name.endswith("kernel"):
+            a = rng.normal(0, 1.0 / np.sqrt(max(np.prod(v.shape[:-1]), 1)), v.shape)
+        else:
+            a = rng.normal(0, jitter, v.shape)
+        a = f32(a)
+        v.assign(a)
+        p[v.name] = H.t64(a).requires_grad_(v.trainable)
+    return p
+
+
+@pytest.mark.parametrize("kind,shape,training", [("enc", (4, 8, 8, 32), True), ("enc", (3, 7, 7, 16), False),
+                                                 ("dec", (4, 4, 4, 32), True), ("dec", (2, 8, 8, 16), False),
+                                                 ("enc", (8, 14, 14, 64), True), ("dec", (8, 7, 7, 128), True)])
+def test_residual_cells(lib_built, kind, shape, training):
+    """EncodingResidualCell (encoder.py:86-107) / GenerativeResidualCell (decoder.py:120-147) fwd + bwd."""
+    from nvae_tf_b200.decoder import GenerativeResidualCell
+    from nvae_tf_b200.encoder import EncodingResidualCell
+    from nvae_tf_b200.runtime import DeviceTensor, Runtime
+    rng = np.random.default_rng(11)
+    rt = Runtime(seed=3)
+    with rt:
+        cell = (EncodingResidualCell if kind == "enc" else GenerativeResidualCell)(shape[-1], name="cell")
+        rt.finalize()
+        p = _load_params(rt, rng)
+        x, dy = f32(rng.normal(0, 1, shape)), f32(rng.normal(0, 1, shape))
+        xt = DeviceTensor(torch.as_tensor(x.astype(np.float32)).to(rt.device))
+        with rt.gradient_tape() as tape:
+            y = cell(xt, training=training)
+        y.grad = torch.as_tensor(dy.astype(np.float32)).to(rt.device)
+        rt.backward(tape)
+    c = O.Ctx(p, training)
+    xo = H.t64(x).requires_grad_(True)
+    yo = (O.encoding_residual_cell if kind == "enc" else O.generative_residual_cell)(c, "cell", xo)
+    leaves = {n: (c.new_stats.get(n, t) if n.endswith("/kernel") else t) for n, t in p.items() if t.requires_grad}
+    grads = torch.autograd.grad(yo, [xo] + list(leaves.values()), H.t64(dy), allow_unused=True)
+    assert H.max_rel_err(npy(y.data), yo.detach().numpy()) < FP32_TOL
+    assert H.max_rel_err(npy(xt.grad), grads[0].numpy()) < FP32_TOL
+    gmax = max(float(g.abs().max()) for g in grads[1:] if g is not None)
+    for (n, _), g in zip(leaves.items(), grads[1:]):
+        want = g.numpy() if g is not None else np.zeros(rt.variables[n].shape)
+        err = H.max_rel_err(npy(rt.variables[n].grad), want, floor=1e-4 * gmax)
+        assert err < FP32_TOL, (n, err)
+    if training:  # SN normalised the kernels in place and advanced u; BN moving statistics moved
+        for n, t in c.new_stats.items():
+            v = rt.variables[n]
+            assert H.max_rel_err(npy(v.value), t.detach().numpy()) < FP32_TOL, n
+
+
+def _make_model(cfg, batch, training, **kw):
+    from nvae_tf_b200.models import NVAE, Adamax, CosineDecay
+    m = NVAE(**H.mirror_kwargs(cfg, batch), training=training, **kw)
+    m.compile(optimizer=Adamax(learning_rate=CosineDecay(1e-3, 1000)), run_eagerly=True)
+    return m
+
+
+def _compare_step(m, f_losses, f_acts, f_grads, f_new, out, recon_t, tol):
+    rt = m.rt
+    total = float(out["loss"].item())
+    assert abs(total - float(f_losses["loss"])) <= TOL_LOSS * abs(float(f_losses["loss"]))
+    assert H.max_rel_err(npy(out["reconstruction_loss"]), f_losses["reconstruction_loss"]) < TOL_LOSS
+    assert H.max_rel_err(npy(out["kl_loss"]), f_losses["kl_loss"], floor=1e-3) < TOL_LOSS
+    assert abs(float(out["bn_loss"].item()) - float(f_losses["bn_loss"])) <= TOL_LOSS * float(f_losses["bn_loss"])
+    assert H.max_rel_err(npy(m.decoder.sampler.kl_all), f_losses["kl_all"]) < TOL_LOSS
+    assert H.max_rel_err(npy(recon_t), f_losses["logits"]) < tol
+    floor = H.grad_floor(f_grads)
+    got = rt.named_grads()
+    worst = ("", 0.0)
+    for n, g in f_grads.items():
+        err = H.max_rel_err(got[n], g, floor)
+        if err > worst[1]:
+            worst = (n, err)
+    assert worst[1] < tol, worst
+    for n, v in f_new.items():
+        assert H.max_rel_err(npy(rt.variables[n].value), v) < tol, n
+
+
+@pytest.mark.parametrize("name", ["tiny_train_balanced", "tiny_infer_beta1"])
+def test_full_step_against_golden_fixture(lib_built, name):
+    f = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = H.oracle_cfg()
+    training, steps = bool(f["training"]), int(f["steps"])
+    x = f["x"]
+    m = _make_model(cfg, x.shape[0], training)
+    rt = m.rt
+    rt.load_named({k[len("param/"):]: f[k] for k in f.files if k.startswith("param/")})
+    n_groups = m.decoder.sampler.n_groups
+    rt.inject_eps([f[f"eps/{i}"] for i in range(n_groups)])
+    m.steps = steps
+    captured = {}
+    orig_call = m.postprocess.__class__.__call__
+
+    def spy(self, inputs, training=False):
+        out = orig_call(self, inputs, training)
+        captured["logits"] = out
+        return out
+    m.postprocess.__class__.__call__ = spy
+    try:
+        out = m.train_step(x, apply_gradients=False)
+    finally:
+        m.postprocess.__class__.__call__ = orig_call
+    losses = {k[5:]: f[k] for k in f.files if k.startswith("loss/")}
+    grads = {k[5:]: f[k] for k in f.files if k.startswith("grad/")}
+    new = {k[4:]: f[k] for k in f.files if k.startswith("new/")}
+    _compare_step(m, losses, None, grads, new, out, captured["logits"].data, FP32_TOL)
+    assert m.steps == steps + 1
+
+
+@pytest.mark.parametrize("batch,steps,training", [(6, 20000, True), (5, 80000, False)])
+def test_default_config_step_against_live_oracle(lib_built, batch, steps, training):
+    """train.py defaults (40.1 M parameters, 15 latent groups), small batch so the float64 oracle runs in seconds."""
+    cfg = O.NVAEConfig()
+    params, trainable, bnl, s = O.build_params(cfg, seed=1, jitter=0.05)
+    params = {k: f32(v) for k, v in params.items()}
+    x = O.make_images(cfg, batch, seed=1).numpy()
+    eps = [f32(e.numpy()) for e in O.make_eps(s, batch, seed=1)]
+    losses, grads, c, record = H.run_oracle_step(cfg, params, trainable, bnl, s, x, eps, steps, training)
+    m = _make_model(cfg, batch, training)
+    m.rt.load_named(params)
+    m.rt.inject_eps(eps)
+    m.steps = steps
+    out = m.train_step(x, apply_gradients=False)
+    assert abs(float(out["loss"].item()) - float(losses["loss"])) <= TOL_LOSS * abs(float(losses["loss"]))
+    assert H.max_rel_err(npy(out["reconstruction_loss"]), losses["reconstruction_loss"]) < TOL_LOSS
+    assert H.max_rel_err(npy(out["kl_loss"]), losses["kl_loss"], floor=1e-3) < TOL_LOSS
+    assert H.max_rel_err(npy(m.decoder.sampler.kl_all), losses["kl_all"]) < TOL_LOSS
+    floor = H.grad_floor(grads)
+    got = m.rt.named_grads()
+    worst = max(((n, H.max_rel_err(got[n], g, floor)) for n, g in grads.items()), key=lambda t: t[1])
+    assert worst[1] < TOL_ACT, worst
+    new = {k: v.detach().numpy() for k, v in c.new_stats.items()}
+    for n, v in new.items():
+        assert H.max_rel_err(npy(m.rt.variables[n].value), v) < TOL_ACT, n
+
+
+def test_optimizer_update_and_second_step(lib_built):
+    """apply_gradients: Adamax + CosineDecay on the flat arena == per-variable oracle updates; step 2 still agrees."""
+    cfg = H.oracle_cfg()
+    params, trainable, bnl, s = O.build_params(cfg, seed=6, jitter=0.1)
+    params = {k: f32(v) for k, v in params.items()}
+    x = O.make_images(cfg, 4, seed=6).numpy()
+    m = _make_model(cfg, 4, True)
+    m.rt.load_named(params)
+    cur = dict(params)
+    mom = {n: (np.zeros_like(params[n]), np.zeros_like(params[n])) for n in trainable}
+    for step in range(2):
+        eps = [f32(e.numpy()) for e in O.make_eps(s, 4, seed=10 + step)]
+        m.rt.inject_eps(eps)
+        m.steps = 5 + step
+        out = m.train_step(x)
+        losses, grads, c, _ = H.run_oracle_step(cfg, cur, trainable, bnl, s, x, eps, 5 + step, True)
+        assert abs(float(out["loss"].item()) - float(losses["loss"])) <= TOL_LOSS * abs(float(losses["loss"]))
+        for n, v in c.new_stats.items():
+            cur[n] = v.detach().numpy()
+        lr = O.cosine_decay_lr(step, 1000)
+        for n in trainable:
+            p, mm, vv = O.adamax_update(H.t64(cur[n]), H.t64(grads[n]), H.t64(mom[n][0]), H.t64(mom[n][1]), step + 1, lr)
+            cur[n], mom[n] = p.numpy(), (mm.numpy(), vv.numpy())
+    got = m.rt.named_values()
+    worst = max(((n, H.max_rel_err(got[n], cur[n])) for n in cur), key=lambda t: t[1])
+    # Adamax divides by max|g|: entries whose gradient is round-off noise move by +-lr regardless -> compare loosely
+    assert worst[1] < 5e-3, worst
+
+
+def test_nll_path_and_public_loss_methods(lib_built):
+    """model(x, nll=True) log q / log p sums (decoder.py:69-102), calculate_kl_loss both branches, crop."""
+    cfg = H.oracle_cfg()
+    params, trainable, bnl, s = O.build_params(cfg, seed=8, jitter=0.1)
+    params = {k: f32(v) for k, v in params.items()}
+    x = O.make_images(cfg, 3, seed=8).numpy()
+    eps = [f32(e.numpy()) for e in O.make_eps(s, 3, seed=8)]
+    m = _make_model(cfg, 3, False)
+    m.rt.load_named(params)
+    m.rt.inject_eps(eps)
+    recon, z_params, log_p, log_q = m(x, nll=True)
+    c = O.Ctx(O.to_torch(params, []), False, [H.t64(e) for e in eps])
+    lo, zo, lpo, lqo = O.nvae_call(c, s, H.t64(x), nll=True)
+    assert H.max_rel_err(npy(recon.data), lo.numpy()) < FP32_TOL
+    assert H.max_rel_err(npy(log_p), lpo.numpy()) < TOL_LOSS and H.max_rel_err(npy(log_q), lqo.numpy()) < TOL_LOSS
+    for balancing in (True, False):
+        kl = m.calculate_kl_loss(z_params, balancing)
+        assert H.max_rel_err(npy(kl), O.calculate_kl_loss(cfg, zo, balancing)[0].numpy()) < TOL_LOSS
+    for crop in (False, True):
+        r = m.calculate_recon_loss(x, recon, crop_output=crop)
+        assert H.max_rel_err(npy(r), O.calculate_recon_loss(H.t64(x), lo, crop).numpy()) < TOL_LOSS
+    assert H.max_rel_err(npy(z_params[2].enc_sigma), zo[2].enc_sigma.numpy()) < FP32_TOL
+    assert len(z_params) == 4 and z_params[0].dec_sigma.min().item() == 1.0
+
+
+def test_sampling_matches_oracle(lib_built):
+    """NVAE.sample (models.py:137-178): temperature only scales z0, inference BN, no SN."""
+    cfg = H.oracle_cfg()
+    params, trainable, bnl, s = O.build_params(cfg, seed=9, jitter=0.1)
+    params = {k: f32(v) for k, v in params.items()}
+    n = 5
+    eps = [f32(e.numpy()) for e in O.make_eps(s, n, seed=9)]
+    m = _make_model(cfg, n, False)
+    m.rt.load_named(params)
+    extra = [eps[-1] * 0.5, eps[-1] * -0.25]  # the two PPL draws z1, z2 (models.py:175-176)
+    m.rt.inject_eps(eps + extra)
+    before = m.rt.named_values()
+    images, last_s, z1, z2 = m.sample(n_samples=n, temperature=0.7)
+    probs, _ = O.sample(cfg, s, O.to_torch(params, []), n, 0.7, [H.t64(e) for e in eps])
+    assert H.max_rel_err(npy(images), probs.numpy()) < FP32_TOL
+    assert images.shape == (n, 32, 32, 1) and z1.shape == z2.shape == (n, 8, 8, cfg.n_latent_per_group)
+    after = m.rt.named_values()
+    assert all(np.array_equal(before[k], after[k]) for k in before)  # sampling never mutates weights or statistics
+    img2 = m.sample_with_z(z1, last_s)
+    assert img2.shape == images.shape and float(img2.min()) >= 0 and float(img2.max()) <= 1
+
+
+def test_cuda_graph_replay_equals_eager(lib_built):
+    """The captured whole-step graph reproduces the eager step (same Philox epsilons from device counters)."""
+    cfg = H.oracle_cfg()
+    x = torch.as_tensor(O.make_images(cfg, 4, seed=3).numpy().astype(np.float32))
+    res = []
+    for mode in ("eager", "graph"):
+        m = _make_model(cfg, 4, True, seed=5)
+        if mode == "eager":
+            outs = [m.train_step(x.cuda()) for _ in range(5)]
+            loss = outs[-1]["loss"].item()
+        else:
+            static_in, replay = m.capture_train_step((4, 32, 32, 1), warmup=2)  # 2 eager + 1 captured-not-run
+            static_in.copy_(x)
+            for _ in range(3):
+                out = replay()
+            loss = out["loss"].item()
+            assert m.graph_launches > 100
+        torch.cuda.synchronize()
+        res.append((loss, m.rt.params.clone()))
+    assert np.isfinite(res[0][0]) and np.isfinite(res[1][0])
+    assert res[0][1].shape == res[1][1].shape
