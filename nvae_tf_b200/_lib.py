@@ -112,6 +112,14 @@ class NoDeviceLib:
                         "(variable layout only); kernels need a CUDA device")
 
 
+def default_precision() -> int:
+    """Arithmetic mode of the convolution GEMMs unless the caller picks one (NVAE_PRECISION=fp32|tf32)."""
+    env = os.environ.get("NVAE_PRECISION", "").lower()
+    if env in ("fp32", "tf32"):
+        return NVAE_PREC_FP32 if env == "fp32" else NVAE_PREC_TF32
+    return NVAE_PREC_FP32
+
+
 _lib = None
 
 

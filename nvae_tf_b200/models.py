@@ -180,7 +180,7 @@ class NVAE:
         B = data.shape[0]
         self._sync_counters()
         rt.lib.fill(rt.grads.data_ptr(), rt.grads.numel(), 0.0, rt.stream)
-        self._schedule(advance=apply_gradients)
+        self._schedule(advance=True)
         with rt.gradient_tape() as tape:
             reconstruction, z_params, *_ = self(data, training=self.training)
             recon_loss = self.calculate_recon_loss(data, reconstruction)
@@ -225,12 +225,15 @@ class NVAE:
 
     # ---- CUDA-graph replay of the whole step --------------------------------------------------------
     def capture_train_step(self, batch_shape, warmup: int = 2):
-        """Warm the allocator/workspace eagerly, then capture fill+SN+fwd+loss+bwd+Adamax as one CUDA graph.
-        Returns (static_input, replay) where replay() runs one step on whatever static_input holds."""
+        """Warm the allocator/workspace eagerly, then capture fill+SN+fwd+loss+bwd(+Adamax) as one CUDA graph.
+        Returns (static_input, replay): replay() runs one step on whatever static_input holds.  With more
+        than one rank the graph ends after backward; the NCCL all-reduce and the Adamax launch follow it."""
         rt = self.rt
         static_in = torch.zeros(tuple(batch_shape), device=rt.device)
         if rt.eps_injected is not None:
             raise RuntimeError("graph capture draws epsilon on device (Philox); clear the injected epsilons")
+        world = torch.distributed.get_world_size(self.process_group) if torch.distributed.is_initialized() else 1
+        in_graph = world == 1
         stream = torch.cuda.Stream(device=rt.device)
         stream.wait_stream(torch.cuda.current_stream(rt.device))
         with torch.cuda.stream(stream):
@@ -242,17 +245,53 @@ class NVAE:
         graph = torch.cuda.CUDAGraph()
         launches0 = rt.lib.launches
         with torch.cuda.graph(graph, stream=stream):
-            out = self.train_step(static_in)
-        self.graph_launches = rt.lib.launches - launches0
+            out = self.train_step(static_in, apply_gradients=in_graph)
+        self.steps -= 1  # capture records the launches without running them
+        self._host_metric = self.steps if self.step_based_warmup else self.epoch
+        self.graph_launches = rt.lib.launches - launches0 + (0 if in_graph else 1)
         self._graph = graph
 
         def replay():
             graph.replay()
+            if not in_graph:
+                self.apply_gradients()
             self.steps += 1
             if self.step_based_warmup:
                 self._host_metric = self.steps
             return out
         return static_in, replay
+
+    def make_train_function(self, batch_shape):
+        """Keras `make_train_function` analogue for HOST batches: returns f(host_batch) -> dict of host arrays.
+        Each call copies the batch host->device (pinned staging), replays the captured step and reads the
+        four losses back device->host -- the end-to-end path bench.py's `e2e` measures."""
+        rt = self.rt
+        static_in, replay = self.capture_train_step(batch_shape)
+        staging = torch.empty(tuple(batch_shape), dtype=torch.float32).pin_memory()
+        B = batch_shape[0]
+        host_out = torch.empty(2 * B + 2, dtype=torch.float32).pin_memory()
+        dev_out = torch.empty(2 * B + 2, device=rt.device)
+
+        def train_function(batch):
+            if isinstance(batch, torch.Tensor) and batch.is_pinned():
+                static_in.copy_(batch, non_blocking=True)
+            else:
+                staging.copy_(torch.as_tensor(batch, dtype=torch.float32))
+                static_in.copy_(staging, non_blocking=True)
+            out = replay()
+            dev_out[0:1].copy_(out["loss"].reshape(1))
+            dev_out[1:2].copy_(out["bn_loss"].reshape(1))
+            dev_out[2:2 + B].copy_(out["reconstruction_loss"])
+            dev_out[2 + B:].copy_(out["kl_loss"])
+            host_out.copy_(dev_out, non_blocking=True)
+            torch.cuda.current_stream(rt.device).synchronize()
+            h = host_out.numpy()
+            return {"loss": float(h[0]), "bn_loss": float(h[1]), "reconstruction_loss": h[2:2 + B],
+                    "kl_loss": h[2 + B:]}
+        train_function.static_in, train_function.replay = static_in, replay
+        train_function.h2d_bytes = int(np.prod(batch_shape)) * 4
+        train_function.d2h_bytes = (2 * B + 2) * 4
+        return train_function
 
     # ---- sampling (models.py:137-189) ---------------------------------------------------------------------
     def sample(self, n_samples=16, temperature=1.0, greyscale=True):

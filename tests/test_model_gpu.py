@@ -68,11 +68,10 @@ def test_residual_cells(lib_built, kind, shape, training):
     grads = torch.autograd.grad(yo, [xo] + list(leaves.values()), H.t64(dy), allow_unused=True)
     assert H.max_rel_err(npy(y.data), yo.detach().numpy()) < FP32_TOL
     assert H.max_rel_err(npy(xt.grad), grads[0].numpy()) < FP32_TOL
-    gmax = max(float(g.abs().max()) for g in grads[1:] if g is not None)
-    for (n, _), g in zip(leaves.items(), grads[1:]):
-        want = g.numpy() if g is not None else np.zeros(rt.variables[n].shape)
-        err = H.max_rel_err(npy(rt.variables[n].grad), want, floor=1e-4 * gmax)
-        assert err < FP32_TOL, (n, err)
+    want = {n: (g.numpy() if g is not None else np.zeros(rt.variables[n].shape))
+            for (n, _), g in zip(leaves.items(), grads[1:])}
+    worst = H.compare_grads({n: npy(rt.variables[n].grad) for n in want}, want, FP32_TOL)
+    assert worst[1] < FP32_TOL, worst
     if training:  # SN normalised the kernels in place and advanced u; BN moving statistics moved
         for n, t in c.new_stats.items():
             v = rt.variables[n]
@@ -95,13 +94,7 @@ def _compare_step(m, f_losses, f_acts, f_grads, f_new, out, recon_t, tol):
     assert abs(float(out["bn_loss"].item()) - float(f_losses["bn_loss"])) <= TOL_LOSS * float(f_losses["bn_loss"])
     assert H.max_rel_err(npy(m.decoder.sampler.kl_all), f_losses["kl_all"]) < TOL_LOSS
     assert H.max_rel_err(npy(recon_t), f_losses["logits"]) < tol
-    floor = H.grad_floor(f_grads)
-    got = rt.named_grads()
-    worst = ("", 0.0)
-    for n, g in f_grads.items():
-        err = H.max_rel_err(got[n], g, floor)
-        if err > worst[1]:
-            worst = (n, err)
+    worst = H.compare_grads(rt.named_grads(), f_grads, tol)
     assert worst[1] < tol, worst
     for n, v in f_new.items():
         assert H.max_rel_err(npy(rt.variables[n].value), v) < tol, n
@@ -156,9 +149,7 @@ def test_default_config_step_against_live_oracle(lib_built, batch, steps, traini
     assert H.max_rel_err(npy(out["reconstruction_loss"]), losses["reconstruction_loss"]) < TOL_LOSS
     assert H.max_rel_err(npy(out["kl_loss"]), losses["kl_loss"], floor=1e-3) < TOL_LOSS
     assert H.max_rel_err(npy(m.decoder.sampler.kl_all), losses["kl_all"]) < TOL_LOSS
-    floor = H.grad_floor(grads)
-    got = m.rt.named_grads()
-    worst = max(((n, H.max_rel_err(got[n], g, floor)) for n, g in grads.items()), key=lambda t: t[1])
+    worst = H.compare_grads(m.rt.named_grads(), grads, TOL_ACT)
     assert worst[1] < TOL_ACT, worst
     new = {k: v.detach().numpy() for k, v in c.new_stats.items()}
     for n, v in new.items():
@@ -175,6 +166,7 @@ def test_optimizer_update_and_second_step(lib_built):
     m.rt.load_named(params)
     cur = dict(params)
     mom = {n: (np.zeros_like(params[n]), np.zeros_like(params[n])) for n in trainable}
+    noisy = set()
     for step in range(2):
         eps = [f32(e.numpy()) for e in O.make_eps(s, 4, seed=10 + step)]
         m.rt.inject_eps(eps)
@@ -184,14 +176,25 @@ def test_optimizer_update_and_second_step(lib_built):
         assert abs(float(out["loss"].item()) - float(losses["loss"])) <= TOL_LOSS * abs(float(losses["loss"]))
         for n, v in c.new_stats.items():
             cur[n] = v.detach().numpy()
+        noisy |= H.analytic_zero_grads(grads)
         lr = O.cosine_decay_lr(step, 1000)
         for n in trainable:
             p, mm, vv = O.adamax_update(H.t64(cur[n]), H.t64(grads[n]), H.t64(mom[n][0]), H.t64(mom[n][1]), step + 1, lr)
             cur[n], mom[n] = p.numpy(), (mm.numpy(), vv.numpy())
     got = m.rt.named_values()
-    worst = max(((n, H.max_rel_err(got[n], cur[n])) for n in cur), key=lambda t: t[1])
-    # Adamax divides by max|g|: entries whose gradient is round-off noise move by +-lr regardless -> compare loosely
-    assert worst[1] < 5e-3, worst
+    # Adamax's first updates are ~lr*sign(g) per element, so an element whose gradient is round-off noise
+    # (|g| ~ 1e-7 of the tensor's scale; whole tensors for a bias in front of a training BN, whose gradient is
+    # analytically zero) moves by ~lr in a noise-determined direction -- in TensorFlow as here.  Hence:
+    # every element stays within the total step size, and all but a sliver agree tightly.
+    lr_total = sum(O.cosine_decay_lr(i, 1000) / (1 - 0.9 ** (i + 1)) for i in range(2))
+    loose = noisy | {n for n in cur if n.endswith("moving_mean")}
+    assert noisy
+    for n in cur:
+        diff = np.abs(got[n] - cur[n])
+        assert diff.max() <= 2.0 * lr_total + 1e-6, (n, diff.max())
+        if n not in loose:
+            bad = float((diff > 1e-5 * np.abs(cur[n]).max() + 1e-7).mean())
+            assert bad < 5e-3, (n, bad)
 
 
 def test_nll_path_and_public_loss_methods(lib_built):
