@@ -209,6 +209,13 @@ NVAE_API int nvae_conv2d_dgrad(const NvaeConvDesc* d, const float* dy, const flo
 NVAE_API int nvae_conv2d_wgrad(const NvaeConvDesc* d, const float* x, const float* x2, const float* dy, float* dw,
                       float* dbias, void* ws, size_t ws_bytes, nvae_stream_t stream);
 
+/* Rounds a tensor in place to TF32 (round-to-nearest, ties away: cvt.rna.tf32.f32) so that a tensor-core
+ * convolution consumes it without the truncation bias of feeding raw fp32 bits to kind::tf32.  Used on
+ * conv operands whose producer did not already round them (gradients arriving at nvae_conv2d_dgrad/wgrad). */
+NVAE_API int nvae_round_tf32(float* p, int64_t n, nvae_stream_t stream);
+/* 1 when nvae_conv2d_{fwd,dgrad,wgrad} (which = 0,1,2) would run this descriptor on the tcgen05 path. */
+NVAE_API int nvae_conv2d_uses_tensor_cores(const NvaeConvDesc* d, int which);
+
 /* ------------------------------------------------------------------------------------------
  * Optimizer + schedules.   Replaces: optimizers.Adamax + CosineDecay train.py:128-131,
  * models.py:121-122,128-129.  `counters` (device int64[2]) = {warm-up metric (model.steps or .epoch),

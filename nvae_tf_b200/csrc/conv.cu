@@ -66,3 +66,13 @@ extern "C" int nvae_conv2d_wgrad(const NvaeConvDesc* d, const float* x, const fl
   }
   return NVAE_OK;
 }
+
+extern "C" int nvae_round_tf32(float* p, int64_t n, nvae_stream_t stream) {
+  if (n > 0 && p == nullptr) return NVAE_E_NULLPTR;
+  return nvae_round_tf32_inplace(p, n, stream);
+}
+
+extern "C" int nvae_conv2d_uses_tensor_cores(const NvaeConvDesc* d, int which) {
+  if (nvae_conv_check(d) != NVAE_OK || d->precision == NVAE_PREC_FP32) return 0;
+  return nvae_conv_tc_supported(d, which) ? 1 : 0;
+}

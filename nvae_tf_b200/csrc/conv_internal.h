@@ -25,3 +25,4 @@ int nvae_conv2d_dgrad_tc(const NvaeConvDesc* d, const float* dy, const float* w_
                          int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream);
 int nvae_conv2d_wgrad_tc(const NvaeConvDesc* d, const float* x, const float* x2, const float* dy, float* dw, void* ws,
                          size_t ws_bytes, cudaStream_t stream);
+int nvae_round_tf32_inplace(float* p, int64_t n, cudaStream_t stream);

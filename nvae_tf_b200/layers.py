@@ -46,14 +46,22 @@ class Conv2D(Layer):
             self.kernel = rt.add_variable("kernel", (kh, kw, in_channels, self.filters),
                                           rt.glorot((kh, kw, in_channels, self.filters), fan_in, fan_out))
             self.bias = rt.add_variable("bias", (self.filters,), np.zeros(self.filters)) if use_bias else None
+        # TF32 operand copies of the kernel inside rt.pack (tensor-core modes only; laid out by Runtime.finalize)
+        self.rnd_off = self.tr_off = -1
+        self.sn = None  # the SpectralNormalization wrapper, if any
+        rt.convs.append(self)
 
     def packed_fwd(self):
-        return None
+        """[Cout][tap][Cin] TF32 copy: the K-major B operand of the forward GEMM (None in fp32 mode)."""
+        return self.rt.pack[self.tr_off:].data_ptr() if self.tr_off >= 0 else None
 
     def packed_dgrad(self):
-        return None
+        """HWIO TF32 copy: the K-major B operand of the backward-data GEMM (None in fp32 mode)."""
+        return self.rt.pack[self.rnd_off:].data_ptr() if self.rnd_off >= 0 else None
 
     def __call__(self, x: DeviceTensor, x2=None, residual=None, **kw) -> DeviceTensor:
+        if self.sn is None and self.tr_off >= 0 and not self.rt.sn_done:
+            self.rt.pack_plain(self)  # un-wrapped conv (tests): refresh the operand copies on every call
         return R.conv2d(self.rt, x, self, x2=x2, residual=residual, **kw)
 
 
@@ -68,11 +76,12 @@ class SpectralNormalization(Layer):
             u = np.clip(rt.rng.normal(0, 0.02, size=(1, layer.filters)), -0.04, 0.04)  # TruncatedNormal(0.02)
             self.u = rt.add_variable("u", (1, layer.filters), u, trainable=False)
         self.index = -1
+        layer.sn = self
         rt.sn_convs.append(self)
 
     def __call__(self, x: DeviceTensor, training: bool = False, **kw) -> DeviceTensor:
-        if training and not self.rt.sn_done:
-            self.rt.spectral_normalize_one(self.index)
+        if not self.rt.sn_done and (training or self.layer.tr_off >= 0):
+            self.rt.spectral_normalize_one(self.index, power_iter=training)
         return self.layer(x, **kw)
 
 

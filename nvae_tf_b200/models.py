@@ -133,8 +133,10 @@ class NVAE:
         inputs = self._as_device(inputs)
         training = bool(training)
         did_sn = False
-        if training and not rt.sn_done:  # all 163 power iterations in 4 launches, before any conv runs
-            rt.spectral_normalize_all()
+        if not rt.sn_done and (training or rt.pack is not None):
+            # all 163 power iterations in 4 launches, before any conv runs; in the tensor-core modes the same
+            # pass (or, for inference, its pack-only form) refreshes the TF32 operand copies of the kernels
+            rt.spectral_normalize_all(power_iter=training)
             rt.sn_done = did_sn = True
         try:
             x = self.preprocess(inputs, training)
@@ -295,6 +297,10 @@ class NVAE:
 
     # ---- sampling (models.py:137-189) ---------------------------------------------------------------------
     def sample(self, n_samples=16, temperature=1.0, greyscale=True):
+        with self.rt.weights_ready():
+            return self._sample(n_samples, temperature, greyscale)
+
+    def _sample(self, n_samples, temperature, greyscale):
         rt = self.rt
         dec = self.decoder
         s = R.broadcast_batch(rt, dec.h, n_samples)
@@ -347,8 +353,9 @@ class NVAE:
     def sample_with_z(self, z, s):
         last_gen_layer = self.decoder.groups[-1]
         z = z if isinstance(z, DeviceTensor) else DeviceTensor(z, needs_grad=False)
-        s = last_gen_layer(s, z)
-        reconstruction = self.postprocess(s)
+        with self.rt.weights_ready():
+            s = last_gen_layer(s, z)
+            reconstruction = self.postprocess(s)
         return self._bernoulli_images(reconstruction, True)
 
     # ---- losses (models.py:191-267) -----------------------------------------------------------------

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from contextlib import contextmanager
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -98,9 +99,13 @@ class Runtime:
         else:
             self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
         self.precision = precision
+        # which tensor-core conv operands get an explicit RN-to-TF32 pass when their producer did not round them
+        self.tf32_round = os.environ.get("NVAE_TF32_ROUND", "dy")  # none | dy | all
         self.rng = np.random.default_rng(seed)
         self.variables: Dict[str, Variable] = {}
         self.sn_convs: List["object"] = []  # SpectralNormalization wrappers, registration order
+        self.convs: List["object"] = []     # every Conv2D (owner of the TF32 operand copies in self.pack)
+        self.pack: Optional[torch.Tensor] = None
         self.bn_loss_layers: List["object"] = []
         self._scope: List[str] = []
         self.tape: Optional[List[Callable[[], None]]] = None
@@ -168,6 +173,7 @@ class Runtime:
                 v.grad = self.grads[v.offset:v.offset + v.size].view(v.shape)
             v._init = None
         self.finalized = True
+        self._alloc_packs()
         self._build_sn_tables()
         self._build_bn_loss_tables()
         self.zero = torch.zeros(8, device=self.device)
@@ -284,6 +290,50 @@ class Runtime:
         self.eps_i += 1
         return out
 
+    # ---- TF32 operand copies of the conv kernels (tensor-core modes) -----------------------------------
+    def _alloc_packs(self) -> None:
+        """Two TF32-rounded copies per Conv2D kernel: HWIO (dgrad B operand) and [Cout][tap][Cin] (forward B
+        operand).  They are rewritten by nvae_spectral_norm's last pass whenever the weights change."""
+        if self.precision == _lib.NVAE_PREC_FP32 or not self.convs:
+            return
+        off = 0
+        for conv in self.convs:
+            n = (conv.kernel.size + 3) // 4 * 4
+            conv.rnd_off, conv.tr_off = off, off + n
+            off += 2 * n
+        self.pack = torch.zeros(max(off, 4), device=self.device)
+        self._plain_tables: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    def _sn_layer_entry(self, L, k, u_off: int, ws_off: int, conv) -> int:
+        rows, cout = k.size // k.shape[-1], k.shape[-1]
+        nch = -(-rows // _lib.SN_ROWS_PER_CHUNK)
+        L.w_off, L.u_off = k.offset, u_off
+        L.v_off = ws_off
+        ws_off += (rows + 3) // 4 * 4
+        L.t_off = ws_off
+        ws_off += nch * (cout + 1)
+        ws_off = (ws_off + 3) // 4 * 4
+        L.rnd_off, L.tr_off = conv.rnd_off, conv.tr_off
+        L.rows, L.cout = rows, cout
+        L.taps, L.cin = k.shape[0] * k.shape[1], k.shape[2]
+        L.cin_pad, L.cout_pad = k.shape[2], cout
+        L.n_chunks = nch
+        return ws_off
+
+    def pack_plain(self, conv) -> None:
+        """Refresh the operand copies of a Conv2D that is not SN-wrapped (pack-only pass, no power iteration)."""
+        key = id(conv)
+        if key not in self._plain_tables:
+            one = (NvaeSnLayer * 1)()
+            self._sn_layer_entry(one[0], conv.kernel, 0, 0, conv)
+            one[0].chunk0 = 0
+            dev = torch.frombuffer(bytearray(bytes(one)), dtype=torch.uint8).to(self.device)
+            cl = torch.zeros(one[0].n_chunks, dtype=torch.int32, device=self.device)
+            self._plain_tables[key] = (dev, cl)
+        dev, cl = self._plain_tables[key]
+        self.lib.spectral_norm(self.params.data_ptr(), self.state.data_ptr(), self.pack.data_ptr(), dev.data_ptr(), 1,
+                               cl.data_ptr(), cl.numel(), 0, 0, None, None, self.stream)
+
     # ---- spectral normalisation tables (SURVEY A.2) -------------------------------------------------
     def _build_sn_tables(self) -> None:
         n = len(self.sn_convs)
@@ -294,22 +344,10 @@ class Runtime:
         chunk_layer: List[int] = []
         ws_off = 0
         for i, sn in enumerate(self.sn_convs):
-            k, u = sn.layer.kernel, sn.u
-            rows, cout = k.size // k.shape[-1], k.shape[-1]
-            nch = -(-rows // _lib.SN_ROWS_PER_CHUNK)
             L = arr[i]
-            L.w_off, L.u_off = k.offset, u.offset
-            L.v_off = ws_off
-            ws_off += (rows + 3) // 4 * 4
-            L.t_off = ws_off
-            ws_off += nch * (cout + 1)
-            ws_off = (ws_off + 3) // 4 * 4
-            L.rnd_off = L.tr_off = -1
-            L.rows, L.cout = rows, cout
-            L.taps, L.cin = k.shape[0] * k.shape[1], k.shape[2]
-            L.cin_pad, L.cout_pad = k.shape[2], cout
-            L.chunk0, L.n_chunks = len(chunk_layer), nch
-            chunk_layer += [i] * nch
+            ws_off = self._sn_layer_entry(L, sn.layer.kernel, sn.u.offset, ws_off, sn.layer)
+            L.chunk0 = len(chunk_layer)
+            chunk_layer += [i] * L.n_chunks
             sn.index = i
         self.sn_host = arr
         self.sn_layers_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
@@ -318,15 +356,35 @@ class Runtime:
         self.sn_sigma = torch.ones(n, device=self.device)
         self._sn_single: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
 
-    def spectral_normalize_all(self) -> None:
-        """One power iteration + in-place W/sigma for every SN-wrapped conv (4 launches total)."""
-        if self.sn_n == 0:
-            return
-        self.lib.spectral_norm(self.params.data_ptr(), self.state.data_ptr(), None, self.sn_layers_dev.data_ptr(),
-                               self.sn_n, self.sn_chunk_layer.data_ptr(), self.sn_chunk_layer.numel(), 1, 0,
-                               self.sn_sigma.data_ptr(), self.sn_ws.data_ptr(), self.stream)
+    def _pack_ptr(self):
+        return self.pack.data_ptr() if self.pack is not None else None
 
-    def spectral_normalize_one(self, index: int) -> None:
+    def spectral_normalize_all(self, power_iter: bool = True) -> None:
+        """One power iteration + in-place W/sigma for every SN-wrapped conv (4 launches total) and, in the
+        tensor-core modes, the refresh of the TF32 operand copies.  power_iter=False only refreshes the copies
+        (inference: SN inactive)."""
+        if self.sn_n == 0 or (not power_iter and self.pack is None):
+            return
+        self.lib.spectral_norm(self.params.data_ptr(), self.state.data_ptr(), self._pack_ptr(),
+                               self.sn_layers_dev.data_ptr(), self.sn_n, self.sn_chunk_layer.data_ptr(),
+                               self.sn_chunk_layer.numel(), int(power_iter), 0, self.sn_sigma.data_ptr(),
+                               self.sn_ws.data_ptr(), self.stream)
+
+    @contextmanager
+    def weights_ready(self):
+        """Inference entry points (NVAE.sample, sample_with_z): refresh the TF32 operand copies once (the
+        optimizer may have moved the weights since) and mark them valid for the enclosed layer calls."""
+        if self.sn_done or self.pack is None:
+            yield
+            return
+        self.spectral_normalize_all(power_iter=False)
+        self.sn_done = True
+        try:
+            yield
+        finally:
+            self.sn_done = False
+
+    def spectral_normalize_one(self, index: int, power_iter: bool = True) -> None:
         """Per-layer path for layers called outside NVAE.call (cell micro-benchmarks, tests)."""
         if index not in self._sn_single:
             one = (NvaeSnLayer * 1)()
@@ -336,8 +394,9 @@ class Runtime:
             cl = torch.zeros(one[0].n_chunks, dtype=torch.int32, device=self.device)
             self._sn_single[index] = (dev, cl)
         dev, cl = self._sn_single[index]
-        self.lib.spectral_norm(self.params.data_ptr(), self.state.data_ptr(), None, dev.data_ptr(), 1, cl.data_ptr(),
-                               cl.numel(), 1, 0, self.sn_sigma[index:].data_ptr(), self.sn_ws.data_ptr(), self.stream)
+        self.lib.spectral_norm(self.params.data_ptr(), self.state.data_ptr(), self._pack_ptr(), dev.data_ptr(), 1,
+                               cl.data_ptr(), cl.numel(), int(power_iter), 0, self.sn_sigma[index:].data_ptr(),
+                               self.sn_ws.data_ptr(), self.stream)
 
     # ---- BN-gamma regulariser tables (models.py:252-267) -----------------------------------------
     def _build_bn_loss_tables(self) -> None:
@@ -428,6 +487,12 @@ def conv2d(rt: Runtime, x: DeviceTensor, conv, x2: Optional[DeviceTensor] = None
     y = out if out is not None else DeviceTensor(rt.empty(d.N, d.Ho, d.Wo, d.Cout))
     ws, wsb = rt.workspace(rt.lib._nvae_conv2d_ws_bytes(C.byref(d), 0))
     bias = conv.bias
+    tc = [bool(rt.lib._nvae_conv2d_uses_tensor_cores(C.byref(d), i)) for i in range(3)] \
+        if rt.precision != _lib.NVAE_PREC_FP32 else [False] * 3
+    if rt.tf32_round == "all" and (tc[0] or tc[2]):
+        for t in (x, x2):
+            if t is not None:
+                rt.lib.round_tf32(t.ptr(), t.data.numel(), rt.stream)
     rt.lib.conv2d_fwd(C.byref(d), x.ptr(), x2.ptr() if x2 is not None else None, k.ptr(), conv.packed_fwd(),
                       bias.ptr() if bias is not None else None, residual.ptr() if residual is not None else None,
                       y.ptr(), ws, wsb, rt.stream)
@@ -436,6 +501,8 @@ def conv2d(rt: Runtime, x: DeviceTensor, conv, x2: Optional[DeviceTensor] = None
             dy = y.grad
             if dy is None:
                 raise RuntimeError(f"conv {k.name}: output has no gradient")
+            if rt.tf32_round != "none" and (tc[1] or tc[2]):
+                rt.lib.round_tf32(dy.data_ptr(), dy.numel(), rt.stream)
             ws, wsb = rt.workspace(rt.lib._nvae_conv2d_ws_bytes(C.byref(d), 2))
             rt.lib.conv2d_wgrad(C.byref(d), x.ptr(), x2.ptr() if x2 is not None else None, dy.data_ptr(), k.gptr(),
                                 bias.gptr() if bias is not None else None, ws, wsb, rt.stream)
