@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--precision", default=os.environ.get("NVAE_PRECISION", "auto"), choices=["auto", "fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("NVAE_PRECISION", "auto"), choices=["auto", "fp32", "tf32", "tf32x3"])
     ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -215,7 +215,7 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    precision = {"fp32": _lib.NVAE_PREC_FP32, "tf32": _lib.NVAE_PREC_TF32,
+    precision = {"fp32": _lib.NVAE_PREC_FP32, "tf32": _lib.NVAE_PREC_TF32, "tf32x3": _lib.NVAE_PREC_TF32X3,
                  "auto": _lib.default_precision()}[args.precision]
     B = args.batch
     model = NVAE(**mirror_kwargs(B), training=True, precision=precision, seed=1)

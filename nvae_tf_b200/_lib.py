@@ -113,11 +113,10 @@ class NoDeviceLib:
 
 
 def default_precision() -> int:
-    """Arithmetic mode of the convolution GEMMs unless the caller picks one (NVAE_PRECISION=fp32|tf32)."""
+    """Arithmetic mode of the convolution GEMMs unless the caller picks one (NVAE_PRECISION=fp32|tf32|tf32x3).
+    Default: 3xTF32 -- tcgen05 tensor cores at fp32-level accuracy (the reference computes in fp32)."""
     env = os.environ.get("NVAE_PRECISION", "").lower()
-    if env in ("fp32", "tf32"):
-        return NVAE_PREC_FP32 if env == "fp32" else NVAE_PREC_TF32
-    return NVAE_PREC_FP32
+    return {"fp32": NVAE_PREC_FP32, "tf32": NVAE_PREC_TF32, "tf32x3": NVAE_PREC_TF32X3}.get(env, NVAE_PREC_TF32X3)
 
 
 _lib = None

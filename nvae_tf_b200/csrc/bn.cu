@@ -102,24 +102,49 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float* __res
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t rows, int64_t rows_per_split,
-                                   int C, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ mm, float* __restrict__ mv, int training, float momentum,
-                                   float eps, float* __restrict__ stat) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float mean, var;
+// Combines the per-CTA (mean, M2) partials: block = 32 channels x 8 split lanes, two passes of plain sums
+// (mean = sum n_s*m_s / n;  M2 = sum q_s + n_s*(m_s - mean)^2) so no serial chain of divisions; fixed order.
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t rows,
+                                                          int64_t rows_per_split, int C,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ mm,
+                                                          float* __restrict__ mv, int training, float momentum,
+                                                          float eps, float* __restrict__ stat) {
+  __shared__ double sm[8][33];
+  const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const bool ok = c < C;
+  float mean = 0.f, var = 1.f;
   if (training) {
-    double n = 0, mu = 0, M2 = 0;
-    for (int s = 0; s < nsplit; ++s) {  // Chan et al. pairwise combine, fixed order
-      const int64_t r0 = (int64_t)s * rows_per_split;
-      const double nb = (double)((r0 + rows_per_split < rows ? r0 + rows_per_split : rows) - r0);
-      const double mb = part[((int64_t)s * 2) * C + c], qb = part[((int64_t)s * 2 + 1) * C + c];
-      const double d = mb - mu, nt = n + nb;
-      mu += d * nb / nt;
-      M2 += qb + d * d * n * nb / nt;
-      n = nt;
-    }
+    const double n = (double)rows;
+    double acc = 0;
+    if (ok)
+      for (int s = sy; s < nsplit; s += 8) {
+        const int64_t r0 = (int64_t)s * rows_per_split;
+        const double nb = (double)((r0 + rows_per_split < rows ? r0 + rows_per_split : rows) - r0);
+        acc += nb * part[((int64_t)s * 2) * C + c];
+      }
+    sm[sy][cx] = acc;
+    __syncthreads();
+    double mu = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mu += sm[k][cx];
+    mu /= n;
+    __syncthreads();
+    acc = 0;
+    if (ok)
+      for (int s = sy; s < nsplit; s += 8) {
+        const int64_t r0 = (int64_t)s * rows_per_split;
+        const double nb = (double)((r0 + rows_per_split < rows ? r0 + rows_per_split : rows) - r0);
+        const double d = part[((int64_t)s * 2) * C + c] - mu;
+        acc += part[((int64_t)s * 2 + 1) * C + c] + nb * d * d;
+      }
+    sm[sy][cx] = acc;
+    __syncthreads();
+    if (sy != 0 || !ok) return;
+    double M2 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) M2 += sm[k][cx];
     mean = (float)mu;
     var = (float)(M2 / n);
     if (mm != nullptr) {
@@ -128,6 +153,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ part, int nsplit, 
       mv[c] = mv[c] * momentum + (float)unbiased * (1.f - momentum);
     }
   } else {
+    if (sy != 0 || !ok) return;
     mean = mm[c];
     var = mv[c];
   }
@@ -244,16 +270,25 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const float* 
 }
 
 // bstat: [2][C] floats: mean(g), mean(g*xhat)
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t rows, int C,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ bstat) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const double* __restrict__ part, int nsplit,
+                                                              int64_t rows, int C, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, float* __restrict__ bstat) {
+  __shared__ double sm[2][8][33];
+  const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   double sg = 0, sq = 0;
-  for (int s = 0; s < nsplit; ++s) {
-    sg += part[((int64_t)s * 2) * C + c];
-    sq += part[((int64_t)s * 2 + 1) * C + c];
-  }
+  if (c < C)
+    for (int s = sy; s < nsplit; s += 8) {
+      sg += part[((int64_t)s * 2) * C + c];
+      sq += part[((int64_t)s * 2 + 1) * C + c];
+    }
+  sm[0][sy][cx] = sg;
+  sm[1][sy][cx] = sq;
+  __syncthreads();
+  if (sy != 0 || c >= C) return;
+  sg = sq = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sg += sm[0][k][cx]; sq += sm[1][k][cx]; }
   if (dgamma) dgamma[c] = (float)sq;
   if (dbeta) dbeta[c] = (float)sg;
   bstat[c] = (float)(sg / (double)rows);
@@ -330,7 +365,7 @@ extern "C" int nvae_bn_stats(const float* x, int64_t rows, int C, const float* g
     bn_stats_kernel<<<dim3(g.nchunk, g.nsplit), kBnThreads, 0, stream>>>(x, rows, C, g.rows_per_split, g.LC, part);
     NVAE_RETURN_IF_LAUNCH_FAILED();
   }
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, g.nsplit, rows, g.rows_per_split, C, gamma, beta,
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, stream>>>(part, g.nsplit, rows, g.rows_per_split, C, gamma, beta,
                                                            moving_mean, moving_var, training, momentum, eps, stat);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
@@ -375,7 +410,7 @@ static int bn_act_bwd_impl(const float* dout, const float* x, int64_t rows, int 
     bn_bwd_reduce_kernel<ACT><<<dim3(g.nchunk, g.nsplit), kBnThreads, 0, stream>>>(dout, x, rows, C, g.rows_per_split,
                                                                                   g.LC, stat, up_h, up_w, part);
     NVAE_RETURN_IF_LAUNCH_FAILED();
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, g.nsplit, rows, C, dgamma, dbeta, bs);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, stream>>>(part, g.nsplit, rows, C, dgamma, dbeta, bs);
     NVAE_RETURN_IF_LAUNCH_FAILED();
     if (training) bstat = bs;
   }

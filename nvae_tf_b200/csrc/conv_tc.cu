@@ -157,6 +157,7 @@ struct GemmParams {
   int k2_base;                  // K index of source 2's first channel inside one tap (= Cin)
   int bk_tap, br_tap;           // B box origin of tap t: (t*bk_tap + k, t*br_tap + n0)
   int BN, stages;
+  int passes;                   // 1: TF32;  3: 3xTF32 = (A_hi,B_lo) + (A_lo,B_hi) + (A_hi,B_hi), small terms first
   // epilogue
   int n_valid, n_split;         // columns < n_split -> out1, [n_split, n_valid) -> out2
   float* out1;
@@ -167,9 +168,13 @@ struct GemmParams {
   int accumulate;
 };
 
+// index: operand (0 = A source 1, 1 = A source 2, 2 = B) * 2 + plane (0 = value, 1 = low-order TF32 part)
+struct TmapSet {
+  CUtensorMap m[6];
+};
+
 __global__ void __launch_bounds__(kThreads, 1)
-conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
-                    const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+conv_gemm_tc_kernel(const __grid_constant__ TmapSet maps, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw);
   const uint32_t stage_base = (smem_u32(smem_raw) + (uint32_t)sizeof(SmemCtl) + 1023u) & ~1023u;
@@ -181,7 +186,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_con
   int n0, h0;
   if (p.tn > 1) { n0 = mt * p.tn; h0 = 0; }
   else { n0 = mt / p.tiles_h; h0 = (mt - n0 * p.tiles_h) * p.th; }
-  const int total = p.taps * (p.nchunk1 + p.nchunk2);
+  const int total = p.passes * p.taps * (p.nchunk1 + p.nchunk2);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
@@ -191,8 +196,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_con
     mbar_init(smem_u32(&ctl->acc_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tma_prefetch_desc(&map_a1);
-    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&maps.m[0]);
+    tma_prefetch_desc(&maps.m[4]);
   }
   if (warp == 1) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols_for(p.BN));
   tc_fence_before();
@@ -204,25 +209,28 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_con
     if (lane == 0) {
       const uint32_t tx = (uint32_t)(p.tw * p.th * p.tn) * 128u + b_bytes;
       int it = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const int r = tap / p.S, s = tap - r * p.S;
-        const int ah = h0 + p.off_h + p.dir * r, aw = p.off_w + p.dir * s;
-        for (int c = 0; c < p.nchunk1 + p.nchunk2; ++c, ++it) {
-          const int st = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          mbar_wait(smem_u32(&ctl->empty[st]), ph ^ 1u);
-          const uint32_t full = smem_u32(&ctl->full[st]);
-          const uint32_t sa = stage_base + (uint32_t)st * stage_bytes;
-          mbar_expect_tx(full, tx);
-          int kk;
-          if (c < p.nchunk1) {
-            tma_load_4d(sa, &map_a1, full, c * kChunk, aw, ah, n0);
-            kk = c * kChunk;
-          } else {
-            tma_load_4d(sa, &map_a2, full, (c - p.nchunk1) * kChunk, aw, ah, n0);
-            kk = p.k2_base + (c - p.nchunk1) * kChunk;
+      for (int pass = 0; pass < p.passes; ++pass) {
+        const int a_lo = (p.passes == 3 && pass == 1), b_lo = (p.passes == 3 && pass == 0);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int r = tap / p.S, s = tap - r * p.S;
+          const int ah = h0 + p.off_h + p.dir * r, aw = p.off_w + p.dir * s;
+          for (int c = 0; c < p.nchunk1 + p.nchunk2; ++c, ++it) {
+            const int st = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            mbar_wait(smem_u32(&ctl->empty[st]), ph ^ 1u);
+            const uint32_t full = smem_u32(&ctl->full[st]);
+            const uint32_t sa = stage_base + (uint32_t)st * stage_bytes;
+            mbar_expect_tx(full, tx);
+            int kk;
+            if (c < p.nchunk1) {
+              tma_load_4d(sa, &maps.m[a_lo], full, c * kChunk, aw, ah, n0);
+              kk = c * kChunk;
+            } else {
+              tma_load_4d(sa, &maps.m[2 + a_lo], full, (c - p.nchunk1) * kChunk, aw, ah, n0);
+              kk = p.k2_base + (c - p.nchunk1) * kChunk;
+            }
+            tma_load_2d(sa + a_bytes, &maps.m[4 + b_lo], full, tap * p.bk_tap + kk, tap * p.br_tap + nt * p.BN);
           }
-          tma_load_2d(sa + a_bytes, &map_b, full, tap * p.bk_tap + kk, tap * p.br_tap + nt * p.BN);
         }
       }
     }
@@ -308,13 +316,14 @@ struct WgradParams {
   int nchunk1, nchunk2, njobs;  // job = (tap, 32-channel chunk); 4 jobs per M tile
   int Cin, Cin2, Ct, Cout;
   int BN, stages;
+  int passes;                   // 1 or 3 (x_hi*dy_lo, x_lo*dy_hi, x_hi*dy_hi)
   float* out;                   // dw (HWIO) or the [splits][taps*Ct][Cout] partial buffer
   int64_t split_stride;         // elements between partials (0 when not split)
 };
 
+// maps: x source 1 {value, lo}, x source 2 {value, lo}, dy {value, lo}
 __global__ void __launch_bounds__(kThreads, 1)
-conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
-                     const __grid_constant__ CUtensorMap map_dy, const WgradParams p) {
+conv_wgrad_tc_kernel(const __grid_constant__ TmapSet maps, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw);
   const uint32_t stage_base = (smem_u32(smem_raw) + (uint32_t)sizeof(SmemCtl) + 1023u) & ~1023u;
@@ -326,7 +335,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_co
   const int nch = p.nchunk1 + p.nchunk2;
   const int pt0 = split * p.ptiles_per_split;
   const int pt1 = min(pt0 + p.ptiles_per_split, p.n_ptiles);
-  const int total = pt1 - pt0;
+  const int npt = pt1 - pt0;
+  const int total = npt * p.passes;
   int njob = p.njobs - mt * 4;
   njob = njob > 4 ? 4 : njob;
 
@@ -338,8 +348,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_co
     mbar_init(smem_u32(&ctl->acc_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tma_prefetch_desc(&map_x1);
-    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&maps.m[0]);
+    tma_prefetch_desc(&maps.m[4]);
   }
   if (warp == 1) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols_for(p.BN));
   tc_fence_before();
@@ -361,7 +371,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_co
       }
       const uint32_t tx = (uint32_t)(njob + nb) * box_bytes;
       for (int it = 0; it < total; ++it) {
-        const int pt = pt0 + it;
+        const int pass = it / npt;
+        const int x_lo = (p.passes == 3 && pass == 1), dy_lo = (p.passes == 3 && pass == 0);
+        const int pt = pt0 + (it - pass * npt);
         int n0, h0;
         if (p.tn > 1) { n0 = pt * p.tn; h0 = 0; }
         else { n0 = pt / p.tiles_h; h0 = (pt - n0 * p.tiles_h) * p.th; }
@@ -372,9 +384,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_co
         const uint32_t sa = stage_base + (uint32_t)st * stage_bytes;
         mbar_expect_tx(full, tx);
         for (int j = 0; j < njob; ++j)
-          tma_load_4d(sa + (uint32_t)j * box_bytes, js[j] ? &map_x2 : &map_x1, full, jc[j], jw[j], h0 + jh[j], n0);
+          tma_load_4d(sa + (uint32_t)j * box_bytes, &maps.m[2 * js[j] + x_lo], full, jc[j], jw[j], h0 + jh[j], n0);
         for (int b = 0; b < nb; ++b)
-          tma_load_4d(sa + a_bytes + (uint32_t)b * box_bytes, &map_dy, full, nt * p.BN + b * kChunk, 0, h0, n0);
+          tma_load_4d(sa + a_bytes + (uint32_t)b * box_bytes, &maps.m[4 + dy_lo], full, nt * p.BN + b * kChunk, 0, h0,
+                      n0);
       }
     }
   } else if (warp == 1) {
@@ -449,6 +462,23 @@ __global__ void round_tf32_kernel(float* __restrict__ p, int64_t n4) {
     float4 v = *reinterpret_cast<float4*>(p + 4 * i);
     v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
     stg4(p + 4 * i, v);
+  }
+}
+
+// lo = tf32_rn(v - trunc_tf32(v)): kind::tf32 reads only the top 19 bits of v (truncation), so v ~= trunc(v) + lo
+// to ~2^-21 relative and  a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  (3xTF32, fp32-level products).
+// v is a [rows][C] view with leading dimension ld; lo is compact [rows][C].
+__global__ void tf32_split_kernel(const float* __restrict__ v, int64_t n4, int C4, int ld, float* __restrict__ lo) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / C4;
+    const int c4 = (int)(i - row * C4);
+    const float4 a = ldg4(v + row * ld + 4 * c4);
+    float4 o;
+    o.x = round_tf32(a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u));
+    o.y = round_tf32(a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u));
+    o.z = round_tf32(a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u));
+    o.w = round_tf32(a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u));
+    stg4(lo + 4 * i, o);
   }
 }
 
@@ -589,6 +619,43 @@ int set_smem_attr(K kernel) {
   return NVAE_OK;
 }
 
+size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// Workspace layout (bytes): [wgrad split-K partials][x lo][x2 lo][dy lo]; the lo planes exist in 3xTF32 mode only.
+struct WsPlan { size_t part, x_lo, x2_lo, dy_lo, total; };
+
+WsPlan plan_ws(const NvaeConvDesc* d, int which, int splits) {
+  WsPlan w{};
+  const bool x3 = d->precision == NVAE_PREC_TF32X3;
+  const size_t pix = (size_t)d->N * d->H * d->W;
+  size_t off = 0;
+  w.part = off;
+  if (which == 2 && splits > 1) off += al256((size_t)splits * d->R * d->S * (d->Cin + d->Cin2) * d->Cout * sizeof(float));
+  w.x_lo = off;
+  if (x3 && which != 1) off += al256(pix * d->Cin * sizeof(float));
+  w.x2_lo = off;
+  if (x3 && which != 1) off += al256(pix * d->Cin2 * sizeof(float));
+  w.dy_lo = off;
+  if (x3 && which != 0) off += al256(pix * d->Cout * sizeof(float));
+  w.total = off;
+  return w;
+}
+
+int split_lo(const float* v, int64_t rows, int C, int ld, float* lo, cudaStream_t stream) {
+  const int64_t n4 = rows * (C / 4);
+  if (n4 <= 0) return NVAE_OK;
+  int64_t g = ceil_div(n4, 256);
+  if (g > kNumSMs * 16) g = kNumSMs * 16;
+  tf32_split_kernel<<<(int)g, 256, 0, stream>>>(v, n4, C / 4, ld, lo);
+  NVAE_RETURN_IF_LAUNCH_FAILED();
+  return NVAE_OK;
+}
+
+// plane 1 (low-order parts) of a packed weight copy follows plane 0 at this element offset
+int64_t weight_plane(const NvaeConvDesc* d) {
+  return round_up((int64_t)d->R * d->S * (d->Cin + d->Cin2) * d->Cout, 4);
+}
+
 }  // namespace
 
 bool nvae_conv_tc_supported(const NvaeConvDesc* d, int which) {
@@ -600,19 +667,26 @@ bool nvae_conv_tc_supported(const NvaeConvDesc* d, int which) {
 }
 
 size_t nvae_conv_tc_ws_bytes(const NvaeConvDesc* d, int which) {
-  if (which != 2 || !common_ok(d)) return 0;
-  WgradPlan w;
-  if (!plan_wgrad(d, &w) || w.splits <= 1) return 0;
-  return (size_t)w.splits * d->R * d->S * (d->Cin + d->Cin2) * d->Cout * sizeof(float);
+  if (!common_ok(d)) return 0;
+  int splits = 1;
+  if (which == 2) {
+    WgradPlan w;
+    if (!plan_wgrad(d, &w)) return 0;
+    splits = w.splits;
+  }
+  return plan_ws(d, which, splits).total;
 }
 
 int nvae_conv2d_fwd_tc(const NvaeConvDesc* d, const float* x, const float* x2, const float* w_tr, const float* bias,
-                       const float* residual, float* y, void*, size_t, cudaStream_t stream) {
+                       const float* residual, float* y, void* ws, size_t ws_bytes, cudaStream_t stream) {
   PixTile t;
   if (!common_ok(d) || !pick_pix_tile(d->N, d->H, d->W, kBM, 1, &t)) return NVAE_E_UNSUPPORTED;
-  if (!aligned16(x) || !aligned16(x2) || !aligned16(w_tr) || !aligned16(bias) || !aligned16(residual) || !aligned16(y))
+  if (!aligned16(x) || !aligned16(x2) || !aligned16(w_tr) || !aligned16(bias) || !aligned16(residual) || !aligned16(y) ||
+      !aligned16(ws))
     return NVAE_E_UNSUPPORTED;
+  const bool x3 = d->precision == NVAE_PREC_TF32X3;
   const int Ct = d->Cin + d->Cin2, taps = d->R * d->S;
+  const int64_t pix = (int64_t)d->N * d->H * d->W;
   GemmParams p{};
   p.N = d->N; p.H = d->H; p.W = d->W;
   p.tw = t.tw; p.th = t.th; p.tn = t.tn; p.tiles_h = t.tiles_h;
@@ -624,35 +698,60 @@ int nvae_conv2d_fwd_tc(const NvaeConvDesc* d, const float* x, const float* x2, c
   p.bk_tap = Ct; p.br_tap = 0;
   p.BN = pick_bn(d->Cout, t.n_tiles, 16);
   p.stages = pick_stages((size_t)kBM * 128 + (size_t)p.BN * 128);
+  p.passes = x3 ? 3 : 1;
   p.n_valid = d->Cout; p.n_split = d->Cout;
   p.out1 = y; p.out2 = nullptr;
   p.ld1 = d->y_ld > 0 ? d->y_ld : d->Cout; p.off1 = d->y_off; p.ld2 = 0;
   p.bias = bias; p.res = residual; p.accumulate = 0;
-  CUtensorMap ma1, ma2, mb;
-  int rc = make_map_nhwc(&ma1, x, d->N, d->H, d->W, d->Cin, d->Cin, t.tw, t.th, t.tn);
+  const float *x_lo = x, *x2_lo = x2, *w_lo = w_tr;
+  if (x3) {
+    const WsPlan wp = plan_ws(d, 0, 1);
+    if (ws == nullptr || ws_bytes < wp.total) return NVAE_E_WORKSPACE;
+    float* l1 = reinterpret_cast<float*>((char*)ws + wp.x_lo);
+    float* l2 = reinterpret_cast<float*>((char*)ws + wp.x2_lo);
+    int rc = split_lo(x, pix, d->Cin, d->Cin, l1, stream);
+    if (rc) return rc;
+    if (d->Cin2 > 0 && (rc = split_lo(x2, pix, d->Cin2, d->Cin2, l2, stream))) return rc;
+    x_lo = l1; x2_lo = l2;
+    w_lo = w_tr + weight_plane(d);
+  }
+  TmapSet maps;
+  int rc = make_map_nhwc(&maps.m[0], x, d->N, d->H, d->W, d->Cin, d->Cin, t.tw, t.th, t.tn);
   if (rc) return rc;
-  if (d->Cin2 > 0) rc = make_map_nhwc(&ma2, x2, d->N, d->H, d->W, d->Cin2, d->Cin2, t.tw, t.th, t.tn);
-  else ma2 = ma1;
+  rc = make_map_nhwc(&maps.m[1], x_lo, d->N, d->H, d->W, d->Cin, d->Cin, t.tw, t.th, t.tn);
   if (rc) return rc;
-  rc = make_map_2d(&mb, w_tr, d->Cout, (int64_t)taps * Ct, p.BN);
+  if (d->Cin2 > 0) {
+    rc = make_map_nhwc(&maps.m[2], x2, d->N, d->H, d->W, d->Cin2, d->Cin2, t.tw, t.th, t.tn);
+    if (rc) return rc;
+    rc = make_map_nhwc(&maps.m[3], x2_lo, d->N, d->H, d->W, d->Cin2, d->Cin2, t.tw, t.th, t.tn);
+    if (rc) return rc;
+  } else {
+    maps.m[2] = maps.m[0]; maps.m[3] = maps.m[1];
+  }
+  rc = make_map_2d(&maps.m[4], w_tr, d->Cout, (int64_t)taps * Ct, p.BN);
+  if (rc) return rc;
+  rc = make_map_2d(&maps.m[5], w_lo, d->Cout, (int64_t)taps * Ct, p.BN);
   if (rc) return rc;
   rc = set_smem_attr(conv_gemm_tc_kernel);
   if (rc) return rc;
   const size_t smem = sizeof(SmemCtl) + 1024 + (size_t)p.stages * ((size_t)kBM * 128 + (size_t)p.BN * 128);
   dim3 grid((unsigned)t.n_tiles, (unsigned)ceil_div(d->Cout, p.BN), 1);
-  conv_gemm_tc_kernel<<<grid, kThreads, smem, stream>>>(ma1, ma2, mb, p);
+  conv_gemm_tc_kernel<<<grid, kThreads, smem, stream>>>(maps, p);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
 
 int nvae_conv2d_dgrad_tc(const NvaeConvDesc* d, const float* dy, const float* w_rnd, float* dx, float* dx2,
-                         int accumulate, void*, size_t, cudaStream_t stream) {
+                         int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream) {
   PixTile t;
   if (!common_ok(d) || !pick_pix_tile(d->N, d->H, d->W, kBM, 1, &t)) return NVAE_E_UNSUPPORTED;
-  if (!aligned16(dy) || !aligned16(w_rnd) || !aligned16(dx) || !aligned16(dx2)) return NVAE_E_UNSUPPORTED;
+  if (!aligned16(dy) || !aligned16(w_rnd) || !aligned16(dx) || !aligned16(dx2) || !aligned16(ws))
+    return NVAE_E_UNSUPPORTED;
   if (dx == nullptr) return NVAE_E_UNSUPPORTED;
+  const bool x3 = d->precision == NVAE_PREC_TF32X3;
   const int Ct = d->Cin + d->Cin2, taps = d->R * d->S;
   const int ld = d->y_ld > 0 ? d->y_ld : d->Cout;
+  const int64_t pix = (int64_t)d->N * d->H * d->W;
   GemmParams p{};
   p.N = d->N; p.H = d->H; p.W = d->W;
   p.tw = t.tw; p.th = t.th; p.tn = t.tn; p.tiles_h = t.tiles_h;
@@ -664,20 +763,37 @@ int nvae_conv2d_dgrad_tc(const NvaeConvDesc* d, const float* dy, const float* w_
   p.bk_tap = 0; p.br_tap = Ct;
   p.BN = pick_bn(Ct, t.n_tiles, 16);
   p.stages = pick_stages((size_t)kBM * 128 + (size_t)p.BN * 128);
+  p.passes = x3 ? 3 : 1;
   p.n_valid = Ct; p.n_split = d->Cin;
   p.out1 = dx; p.out2 = dx2;
   p.ld1 = d->Cin; p.off1 = 0; p.ld2 = d->Cin2;
   p.bias = nullptr; p.res = nullptr; p.accumulate = accumulate;
-  CUtensorMap ma, mb;
-  int rc = make_map_nhwc(&ma, dy + d->y_off, d->N, d->H, d->W, d->Cout, ld, t.tw, t.th, t.tn);
+  TmapSet maps;
+  int rc = make_map_nhwc(&maps.m[0], dy + d->y_off, d->N, d->H, d->W, d->Cout, ld, t.tw, t.th, t.tn);
   if (rc) return rc;
-  rc = make_map_2d(&mb, w_rnd, (int64_t)taps * Ct, d->Cout, p.BN);
+  const float* w_lo = w_rnd;
+  if (x3) {
+    const WsPlan wp = plan_ws(d, 1, 1);
+    if (ws == nullptr || ws_bytes < wp.total) return NVAE_E_WORKSPACE;
+    float* l = reinterpret_cast<float*>((char*)ws + wp.dy_lo);
+    rc = split_lo(dy + d->y_off, pix, d->Cout, ld, l, stream);
+    if (rc) return rc;
+    rc = make_map_nhwc(&maps.m[1], l, d->N, d->H, d->W, d->Cout, d->Cout, t.tw, t.th, t.tn);
+    if (rc) return rc;
+    w_lo = w_rnd + weight_plane(d);
+  } else {
+    maps.m[1] = maps.m[0];
+  }
+  maps.m[2] = maps.m[0]; maps.m[3] = maps.m[1];
+  rc = make_map_2d(&maps.m[4], w_rnd, (int64_t)taps * Ct, d->Cout, p.BN);
+  if (rc) return rc;
+  rc = make_map_2d(&maps.m[5], w_lo, (int64_t)taps * Ct, d->Cout, p.BN);
   if (rc) return rc;
   rc = set_smem_attr(conv_gemm_tc_kernel);
   if (rc) return rc;
   const size_t smem = sizeof(SmemCtl) + 1024 + (size_t)p.stages * ((size_t)kBM * 128 + (size_t)p.BN * 128);
   dim3 grid((unsigned)t.n_tiles, (unsigned)ceil_div(Ct, p.BN), 1);
-  conv_gemm_tc_kernel<<<grid, kThreads, smem, stream>>>(ma, ma, mb, p);
+  conv_gemm_tc_kernel<<<grid, kThreads, smem, stream>>>(maps, p);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -687,9 +803,13 @@ int nvae_conv2d_wgrad_tc(const NvaeConvDesc* d, const float* x, const float* x2,
   WgradPlan w;
   if (!common_ok(d) || !plan_wgrad(d, &w)) return NVAE_E_UNSUPPORTED;
   if (!aligned16(x) || !aligned16(x2) || !aligned16(dy) || !aligned16(dw) || !aligned16(ws)) return NVAE_E_UNSUPPORTED;
+  const bool x3 = d->precision == NVAE_PREC_TF32X3;
   const int Ct = d->Cin + d->Cin2, taps = d->R * d->S;
   const int ld = d->y_ld > 0 ? d->y_ld : d->Cout;
   const int64_t wsize = (int64_t)taps * Ct * d->Cout;
+  const int64_t pix = (int64_t)d->N * d->H * d->W;
+  const WsPlan wp = plan_ws(d, 2, w.splits);
+  if (wp.total > 0 && (ws == nullptr || ws_bytes < wp.total)) return NVAE_E_WORKSPACE;
   WgradParams p{};
   p.N = d->N; p.H = d->H; p.W = d->W;
   p.tw = w.t.tw; p.th = w.t.th; p.tn = w.t.tn; p.KP = w.t.tw * w.t.th * w.t.tn;
@@ -700,28 +820,49 @@ int nvae_conv2d_wgrad_tc(const NvaeConvDesc* d, const float* x, const float* x2,
   p.njobs = w.njobs;
   p.Cin = d->Cin; p.Cin2 = d->Cin2; p.Ct = Ct; p.Cout = d->Cout;
   p.BN = w.BN; p.stages = w.stages;
+  p.passes = x3 ? 3 : 1;
   if (w.splits > 1) {
-    if (ws == nullptr || ws_bytes < (size_t)w.splits * wsize * sizeof(float)) return NVAE_E_WORKSPACE;
-    p.out = reinterpret_cast<float*>(ws);
+    p.out = reinterpret_cast<float*>((char*)ws + wp.part);
     p.split_stride = wsize;
   } else {
     p.out = dw;
     p.split_stride = 0;
   }
-  CUtensorMap mx1, mx2, mdy;
+  const float *x_lo = x, *x2_lo = x2, *dy_hi = dy + d->y_off, *dy_lo = dy_hi;
+  int dy_lo_ld = ld;
+  int rc;
+  if (x3) {
+    float* l1 = reinterpret_cast<float*>((char*)ws + wp.x_lo);
+    float* l2 = reinterpret_cast<float*>((char*)ws + wp.x2_lo);
+    float* l3 = reinterpret_cast<float*>((char*)ws + wp.dy_lo);
+    if ((rc = split_lo(x, pix, d->Cin, d->Cin, l1, stream))) return rc;
+    if (d->Cin2 > 0 && (rc = split_lo(x2, pix, d->Cin2, d->Cin2, l2, stream))) return rc;
+    if ((rc = split_lo(dy_hi, pix, d->Cout, ld, l3, stream))) return rc;
+    x_lo = l1; x2_lo = l2; dy_lo = l3; dy_lo_ld = d->Cout;
+  }
+  TmapSet maps;
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  int rc = make_map_nhwc(&mx1, x, d->N, d->H, d->W, d->Cin, d->Cin, p.tw, p.th, p.tn, swz);
+  rc = make_map_nhwc(&maps.m[0], x, d->N, d->H, d->W, d->Cin, d->Cin, p.tw, p.th, p.tn, swz);
   if (rc) return rc;
-  if (d->Cin2 > 0) rc = make_map_nhwc(&mx2, x2, d->N, d->H, d->W, d->Cin2, d->Cin2, p.tw, p.th, p.tn, swz);
-  else mx2 = mx1;
+  rc = make_map_nhwc(&maps.m[1], x_lo, d->N, d->H, d->W, d->Cin, d->Cin, p.tw, p.th, p.tn, swz);
   if (rc) return rc;
-  rc = make_map_nhwc(&mdy, dy + d->y_off, d->N, d->H, d->W, d->Cout, ld, p.tw, p.th, p.tn, swz);
+  if (d->Cin2 > 0) {
+    rc = make_map_nhwc(&maps.m[2], x2, d->N, d->H, d->W, d->Cin2, d->Cin2, p.tw, p.th, p.tn, swz);
+    if (rc) return rc;
+    rc = make_map_nhwc(&maps.m[3], x2_lo, d->N, d->H, d->W, d->Cin2, d->Cin2, p.tw, p.th, p.tn, swz);
+    if (rc) return rc;
+  } else {
+    maps.m[2] = maps.m[0]; maps.m[3] = maps.m[1];
+  }
+  rc = make_map_nhwc(&maps.m[4], dy_hi, d->N, d->H, d->W, d->Cout, ld, p.tw, p.th, p.tn, swz);
+  if (rc) return rc;
+  rc = make_map_nhwc(&maps.m[5], dy_lo, d->N, d->H, d->W, d->Cout, dy_lo_ld, p.tw, p.th, p.tn, swz);
   if (rc) return rc;
   rc = set_smem_attr(conv_wgrad_tc_kernel);
   if (rc) return rc;
   const size_t smem = sizeof(SmemCtl) + 1024 + (size_t)p.stages * (size_t)(4 + p.BN / kChunk) * p.KP * 128;
   dim3 grid((unsigned)w.m_tiles, (unsigned)w.n_tiles, (unsigned)w.splits);
-  conv_wgrad_tc_kernel<<<grid, kThreads, smem, stream>>>(mx1, mx2, mdy, p);
+  conv_wgrad_tc_kernel<<<grid, kThreads, smem, stream>>>(maps, p);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   if (w.splits > 1) {
     int64_t g = ceil_div(wsize / 4, 256);

@@ -50,8 +50,9 @@ class NVAE:
     def __init__(self, n_encoder_channels, n_decoder_channels, res_cells_per_group, n_preprocess_blocks,
                  n_preprocess_cells, n_latent_per_group, n_latent_scales, n_groups_per_scale, n_postprocess_blocks,
                  n_post_process_cells, sr_lambda, scale_factor, total_epochs, n_total_iterations, step_based_warmup,
-                 input_shape, *, training: bool = True, precision: int = _lib.NVAE_PREC_FP32, seed: int = 1,
+                 input_shape, *, training: bool = True, precision: Optional[int] = None, seed: int = 1,
                  device: Optional[str] = None, process_group=None, **kwargs):
+        precision = _lib.default_precision() if precision is None else precision
         self.rt = rt = Runtime(device=device, precision=precision, seed=seed)
         self.training = training
         self.process_group = process_group

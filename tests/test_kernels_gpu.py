@@ -131,7 +131,7 @@ def test_conv2d_fwd_dgrad_wgrad(rt, case):
     xt, x2t = dev(rt, x), (dev(rt, x2) if Cin2 else None)
     rest = dev(rt, res) if residual else None
     with rt.gradient_tape() as tape:
-        y = R.conv2d(rt, xt, conv, x2=x2t, residual=rest, shift=shift)
+        y = conv(xt, x2=x2t, residual=rest, shift=shift)
     assert y.shape == tuple(yo.shape)
     seed_grad(rt, y, dy)
     rt.backward(tape)
@@ -143,6 +143,65 @@ def test_conv2d_fwd_dgrad_wgrad(rt, case):
         check("dres", npy(rest.grad), reso.grad.numpy())
     check("dw", npy(conv.kernel.grad), wo.grad.numpy())
     check("db", npy(conv.bias.grad), bo.grad.numpy())
+
+
+TC_CASES = [
+    # (N, H, W, Cin, Cin2, Cout, k, residual): stride-1 shapes the tcgen05 path takes
+    (8, 4, 4, 64, 0, 64, 3, False),       # encoder cell conv at the 4x4 scale
+    (4, 8, 8, 128, 0, 128, 3, True),      # ... 8x8 scale, with residual (encoder.py:16 style)
+    (16, 4, 4, 32, 20, 256, 1, False),    # DecoderSampleCombiner concat(h, z0): K = 52, ragged second source
+    (6, 4, 4, 256, 0, 1536, 1, False),    # decoder cell expand 1x1
+    (6, 4, 4, 1536, 0, 256, 1, False),    # decoder cell project 1x1
+    (6, 8, 8, 128, 0, 40, 3, False),      # sampler head, N = 40
+    (2, 16, 16, 64, 0, 96, 5, False),     # postprocess 5x5
+    (3, 14, 14, 64, 0, 64, 3, False),     # BASELINE configs[1] micro-bench shapes
+    (5, 7, 7, 128, 0, 128, 3, False),
+    (2, 32, 32, 32, 0, 32, 3, False),     # W*th tile with two image rows per box
+]
+
+
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 2e-5), ("tf32", 3e-3)])
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv2d_tensor_core_modes(lib_built, case, mode, tol):
+    """tcgen05 implicit-GEMM fwd / dgrad / wgrad against the float64 oracle.  3xTF32 must reach the fp32
+    tolerance; single-pass TF32 is held to the 10-bit-mantissa level."""
+    import ctypes as C
+    from nvae_tf_b200 import _lib
+    from nvae_tf_b200 import runtime as R
+    from nvae_tf_b200.layers import Conv2D
+    N, Hh, W, Cin, Cin2, Cout, k, residual = case
+    prec = {"tf32x3": _lib.NVAE_PREC_TF32X3, "tf32": _lib.NVAE_PREC_TF32}[mode]
+    rng = np.random.default_rng(5)
+    with R.Runtime(seed=7, precision=prec) as rt:
+        conv = Conv2D(Cout, (k, k), padding="same", in_channels=Cin + Cin2, name="c")
+        rt.finalize()
+        w = f32(rng.normal(0, 1.0 / np.sqrt(k * k * (Cin + Cin2)), (k, k, Cin + Cin2, Cout)))
+        b = f32(rng.normal(0, 0.3, Cout))
+        conv.kernel.assign(w)
+        conv.bias.assign(b)
+        x = f32(rng.normal(0, 1, (N, Hh, W, Cin)))
+        x2 = f32(rng.normal(0, 1, (N, Hh, W, Cin2))) if Cin2 else None
+        xo, x2o = H.t64(x).requires_grad_(True), (H.t64(x2).requires_grad_(True) if Cin2 else None)
+        wo, bo = H.t64(w).requires_grad_(True), H.t64(b).requires_grad_(True)
+        yo = O.conv2d(torch.cat((xo, x2o), 3) if Cin2 else xo, wo, bo, 1)
+        res = f32(rng.normal(0, 1, tuple(yo.shape))) if residual else None
+        if residual:
+            yo = yo + H.t64(res)
+        dy = f32(rng.normal(0, 1, tuple(yo.shape)))
+        yo.backward(H.t64(dy))
+        xt, x2t = dev(rt, x), (dev(rt, x2) if Cin2 else None)
+        d = R.conv_desc(rt, xt.shape, Cin2, conv.kernel.shape, 1)
+        assert all(rt.lib._nvae_conv2d_uses_tensor_cores(C.byref(d), i) == 1 for i in range(3)), "not on tcgen05"
+        with rt.gradient_tape() as tape:
+            y = conv(xt, x2=x2t, residual=dev(rt, res) if residual else None)
+        seed_grad(rt, y, dy)
+        rt.backward(tape)
+        check("y", npy(y.data), yo.detach().numpy(), tol)
+        check("dx", npy(xt.grad), xo.grad.numpy(), tol)
+        if Cin2:
+            check("dx2", npy(x2t.grad), x2o.grad.numpy(), tol)
+        check("dw", npy(conv.kernel.grad), wo.grad.numpy(), tol)
+        check("db", npy(conv.bias.grad), bo.grad.numpy(), tol)
 
 
 def test_conv2d_concat_output_and_accumulating_dgrad(rt):

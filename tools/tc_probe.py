@@ -20,6 +20,9 @@ from nvae_tf_b200 import runtime as R  # noqa: E402
 from nvae_tf_b200.layers import Conv2D  # noqa: E402
 
 
+PREC = {"tf32": _lib.NVAE_PREC_TF32, "tf32x3": _lib.NVAE_PREC_TF32X3}[os.environ.get("NVAE_PRECISION", "tf32x3")]
+
+
 def tf32_round(a: np.ndarray) -> np.ndarray:
     """round-to-nearest (ties away) to 10 explicit mantissa bits, like cvt.rna.tf32.f32"""
     u = np.asarray(a, np.float32).view(np.uint32).astype(np.uint64)
@@ -45,7 +48,7 @@ def rel(a, b):
 
 def run_case(N, H, W, Cin, Cin2, Cout, k, exact, seed=0, time_it=False):
     rng = np.random.default_rng(seed)
-    rt = R.Runtime(precision=_lib.NVAE_PREC_TF32, seed=1)
+    rt = R.Runtime(precision=PREC, seed=1)
     with rt:
         conv = Conv2D(Cout, (k, k), padding="same", in_channels=Cin + Cin2, name="c")
         rt.finalize()
