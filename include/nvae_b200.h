@@ -43,9 +43,10 @@ enum {
 
 enum { NVAE_ACT_NONE = 0, NVAE_ACT_SWISH = 1, NVAE_ACT_ELU = 2 };
 
-/* Arithmetic of the convolution GEMMs. FP32 = CUDA-core FFMA (exact-fp32 parity mode);
- * TF32 = tcgen05 kind::tf32 on operands rounded to nearest-even TF32 by their producers;
- * TF32X3 = 3-pass split (hi*hi + hi*lo + lo*hi), ~fp32 accuracy on the tensor cores. */
+/* Arithmetic of the convolution GEMMs. FP32 = CUDA-core FFMA; TF32 = one tcgen05 kind::tf32 MMA per operand
+ * pair, operands rounded to TF32 by their producers (10-bit mantissa: ~5e-4 per conv, NOT within the 1e-3
+ * whole-model parity bound); TF32X3 = 3xTF32 split inside the kernel (a_hi*b_lo + a_lo*b_hi + a_hi*b_hi on the
+ * tensor cores, fp32-level accuracy: the default and the mode every parity claim is made in). */
 enum { NVAE_PREC_FP32 = 0, NVAE_PREC_TF32 = 1, NVAE_PREC_TF32X3 = 2 };
 
 /* Library / device identification. Returns 100 for sm_100; build id string is static. */
@@ -69,10 +70,9 @@ NVAE_API int nvae_bn_stats(const float* x, int64_t rows, int C, const float* gam
 
 /* out = act(x*scale+shift) (stat==NULL: out = act(x)); optional nearest x2 upsample
  * (tf.image.resize "nearest", common.py:168-172: pass up_h=H, up_w=W of x, else 0,0);
- * round_tf32!=0 rounds the result to TF32 (RN) so tcgen05 kind::tf32 consumes it exactly.
- * lo!=NULL additionally stores the TF32-rounded residual out_full-out for the 3-pass mode. */
+ * round_tf32!=0 rounds the result to TF32 (RN) so single-pass kind::tf32 consumes it without truncation bias. */
 NVAE_API int nvae_bn_act_fwd(const float* x, int64_t rows, int C, const float* stat, int act, int up_h, int up_w,
-                    int round_tf32, float* out, float* lo, nvae_stream_t stream);
+                    int round_tf32, float* out, nvae_stream_t stream);
 
 /* Backward of nvae_bn_act_fwd (+ batch-norm backward when stat!=NULL):
  *   g = dout*act'(u)  (summed over the 2x2 replicas when upsampled)
@@ -165,17 +165,18 @@ typedef struct {
   int64_t u_off;    /* u [cout] in `state`                                         */
   int64_t v_off;    /* scratch v_raw [rows] in `ws` (floats)                       */
   int64_t t_off;    /* scratch partial t [n_chunks,cout] in `ws` (floats)          */
-  int64_t rnd_off;  /* TF32-rounded HWIO copy in `pack` (floats) or -1             */
-  int64_t tr_off;   /* TF32-rounded transposed copy [cout_pad][taps][cin_pad] or -1 */
+  int64_t rnd_off;  /* HWIO operand copy in `pack` (floats) or -1                   */
+  int64_t tr_off;   /* transposed operand copy [cout_pad][taps][cin_pad] or -1      */
   int32_t rows, cout, taps, cin, cin_pad, cout_pad;
   int32_t chunk0;   /* first row-chunk index of this layer in the flat chunk list  */
   int32_t n_chunks;
 } NvaeSnLayer;
 #define NVAE_SN_ROWS_PER_CHUNK 64
 /* power_iter!=0: v=l2n(W u), u'=l2n(v W), sigma=(vW).u', W/=sigma, u=u' (in place);
- * power_iter==0: weights left untouched (inference / SN inactive), only (re)packed. */
+ * power_iter==0: weights left untouched (inference / SN inactive), only (re)packed.
+ * pack_exact==0: the operand copies are rounded to TF32 (NVAE_PREC_TF32); !=0: exact fp32 (NVAE_PREC_TF32X3). */
 NVAE_API int nvae_spectral_norm(float* params, float* state, float* pack, const NvaeSnLayer* layers_dev, int n_layers,
-                       const int32_t* chunk_layer_dev, int n_chunks_total, int power_iter, int pack_lo,
+                       const int32_t* chunk_layer_dev, int n_chunks_total, int power_iter, int pack_exact,
                        float* sigma_out, float* ws, nvae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -197,12 +198,13 @@ typedef struct {
 } NvaeConvDesc;
 
 NVAE_API size_t nvae_conv2d_ws_bytes(const NvaeConvDesc* d, int which /*0 fwd,1 dgrad,2 wgrad*/);
-/* y = conv(x ++ x2, w) + bias (+ residual).  w: HWIO fp32 master; w_tr: packed transposed TF32
- * copy from nvae_spectral_norm (tensor-core path; may be NULL for NVAE_PREC_FP32). */
+/* y = conv(x ++ x2, w) + bias (+ residual).  w: HWIO fp32 master; w_tr: the transposed operand copy
+ * [Cout][taps][Cin+Cin2] written by nvae_spectral_norm (tensor-core path; may be NULL for NVAE_PREC_FP32). */
 NVAE_API int nvae_conv2d_fwd(const NvaeConvDesc* d, const float* x, const float* x2, const float* w, const float* w_tr,
                     const float* bias, const float* residual, float* y, void* ws, size_t ws_bytes,
                     nvae_stream_t stream);
-/* dx (+)= dgrad(dy, w) for the first Cin channels, dx2 for the concatenated Cin2 channels. */
+/* dx (+)= dgrad(dy, w) for the first Cin channels, dx2 for the concatenated Cin2 channels.
+ * w_rnd: the HWIO operand copy from nvae_spectral_norm (NVAE_PREC_TF32: TF32-rounded; TF32X3: w itself works). */
 NVAE_API int nvae_conv2d_dgrad(const NvaeConvDesc* d, const float* dy, const float* w, const float* w_rnd, float* dx,
                       float* dx2, int accumulate, void* ws, size_t ws_bytes, nvae_stream_t stream);
 /* dw = wgrad(x ++ x2, dy) (HWIO, '='), dbias = column sums of dy (NULL to skip). */

@@ -166,11 +166,10 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restri
   stat[3 * C + c] = b - mean * scale;
 }
 
-// ---- forward apply + activation (+ nearest x2 upsample, + TF32 rounding / split) -------------
+// ---- forward apply + activation (+ nearest x2 upsample, + TF32 rounding) ---------------------
 template <int ACT>
 __global__ void bn_act_fwd_kernel(const float* __restrict__ x, int64_t n4, int C4, const float* __restrict__ stat,
-                                  int up_h, int up_w, int round_mode, float* __restrict__ out,
-                                  float* __restrict__ lo) {
+                                  int up_h, int up_w, int round_mode, float* __restrict__ out) {
   const int C = C4 * 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
@@ -180,16 +179,9 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ x, int64_t n4, int C
       v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
     }
     v.x = act_fwd<ACT>(v.x); v.y = act_fwd<ACT>(v.y); v.z = act_fwd<ACT>(v.z); v.w = act_fwd<ACT>(v.w);
-    float4 l = make_float4(0, 0, 0, 0);
-    if (round_mode) {
-      float4 r = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
-      if (lo != nullptr)
-        l = make_float4(round_tf32(v.x - r.x), round_tf32(v.y - r.y), round_tf32(v.z - r.z), round_tf32(v.w - r.w));
-      v = r;
-    }
+    if (round_mode) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
     if (up_h == 0) {
       stg4(out + i * 4, v);
-      if (lo != nullptr) stg4(lo + i * 4, l);
     } else {
       const int64_t row = i / C4;
       const int w = (int)(row % up_w);
@@ -199,9 +191,6 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ x, int64_t n4, int C
       const int64_t W2 = 2 * (int64_t)up_w;
       const int64_t o00 = (((n * 2 * up_h + 2 * h) * W2) + 2 * w) * C + c4 * 4;
       stg4(out + o00, v); stg4(out + o00 + C, v); stg4(out + o00 + W2 * C, v); stg4(out + o00 + W2 * C + C, v);
-      if (lo != nullptr) {
-        stg4(lo + o00, l); stg4(lo + o00 + C, l); stg4(lo + o00 + W2 * C, l); stg4(lo + o00 + W2 * C + C, l);
-      }
     }
   }
 }
@@ -372,7 +361,7 @@ extern "C" int nvae_bn_stats(const float* x, int64_t rows, int C, const float* g
 }
 
 extern "C" int nvae_bn_act_fwd(const float* x, int64_t rows, int C, const float* stat, int act, int up_h, int up_w,
-                               int round_tf32, float* out, float* lo, nvae_stream_t stream) {
+                               int round_tf32, float* out, nvae_stream_t stream) {
   if (C <= 0 || (C & 3) || rows <= 0) return NVAE_E_BADSHAPE;
   if (x == nullptr || out == nullptr) return NVAE_E_NULLPTR;
   if ((up_h == 0) != (up_w == 0)) return NVAE_E_BADSHAPE;
@@ -381,13 +370,13 @@ extern "C" int nvae_bn_act_fwd(const float* x, int64_t rows, int C, const float*
   const int grid = ew_grid(n4, 256);
   switch (act) {
     case NVAE_ACT_NONE:
-      bn_act_fwd_kernel<NVAE_ACT_NONE><<<grid, 256, 0, stream>>>(x, n4, C / 4, stat, up_h, up_w, round_tf32, out, lo);
+      bn_act_fwd_kernel<NVAE_ACT_NONE><<<grid, 256, 0, stream>>>(x, n4, C / 4, stat, up_h, up_w, round_tf32, out);
       break;
     case NVAE_ACT_SWISH:
-      bn_act_fwd_kernel<NVAE_ACT_SWISH><<<grid, 256, 0, stream>>>(x, n4, C / 4, stat, up_h, up_w, round_tf32, out, lo);
+      bn_act_fwd_kernel<NVAE_ACT_SWISH><<<grid, 256, 0, stream>>>(x, n4, C / 4, stat, up_h, up_w, round_tf32, out);
       break;
     case NVAE_ACT_ELU:
-      bn_act_fwd_kernel<NVAE_ACT_ELU><<<grid, 256, 0, stream>>>(x, n4, C / 4, stat, up_h, up_w, round_tf32, out, lo);
+      bn_act_fwd_kernel<NVAE_ACT_ELU><<<grid, 256, 0, stream>>>(x, n4, C / 4, stat, up_h, up_w, round_tf32, out);
       break;
     default:
       return NVAE_E_UNSUPPORTED;

@@ -89,14 +89,14 @@ __global__ void __launch_bounds__(kSnThreads) sn_finalize_kernel(float* __restri
 }
 
 // K4: W <- W/sigma (in place), TF32-rounded HWIO copy (dgrad B operand), transposed TF32 copy
-// [cout_pad][taps][cin_pad] (fwd B operand, K-major).  pack_lo: each copy is followed by a second plane holding
-// the TF32-rounded remainders v - tf32(v) (3xTF32 mode).  Transposition goes through shared memory
+// [cout_pad][taps][cin_pad] (fwd B operand, K-major).  pack_exact: the copies keep the full fp32 values (3xTF32
+// mode splits them into high and low parts inside the convolution kernel).  Transposition goes through shared memory
 // so both the read (co fastest) and the write (ci fastest) are coalesced.
 __global__ void __launch_bounds__(kSnThreads) sn_scale_pack_kernel(float* __restrict__ params, float* __restrict__ pack,
                                                                    const NvaeSnLayer* __restrict__ layers,
                                                                    const int32_t* __restrict__ chunk_layer,
                                                                    const float* __restrict__ sigma, int power_iter,
-                                                                   int pack_lo) {
+                                                                   int pack_exact) {
   __shared__ float tile[kSnRows][33];
   const int li = chunk_layer[blockIdx.x];
   const NvaeSnLayer L = layers[li];
@@ -106,7 +106,6 @@ __global__ void __launch_bounds__(kSnThreads) sn_scale_pack_kernel(float* __rest
   const int r0 = chunk * kSnRows;
   const int nr = (L.rows - r0) < kSnRows ? (L.rows - r0) : kSnRows;
   const int K = L.taps * L.cin_pad;
-  const int64_t plane = ((int64_t)L.rows * L.cout + 3) & ~(int64_t)3;  // lo plane follows the value plane
   for (int cb = 0; cb < L.cout; cb += 32) {
     // load [nr][32] tile: threads map co fastest
     for (int i = threadIdx.x; i < kSnRows * 32; i += kSnThreads) {
@@ -116,11 +115,7 @@ __global__ void __launch_bounds__(kSnThreads) sn_scale_pack_kernel(float* __rest
         const int64_t o = (int64_t)(r0 + r) * L.cout + c;
         v = W[o] * inv_sigma;
         if (power_iter) W[o] = v;
-        if (L.rnd_off >= 0) {
-          const float hi = round_tf32(v);
-          pack[L.rnd_off + o] = hi;
-          if (pack_lo) pack[L.rnd_off + plane + o] = round_tf32(v - hi);
-        }
+        if (L.rnd_off >= 0) pack[L.rnd_off + o] = pack_exact ? v : round_tf32(v);
       }
       tile[r][i & 31] = v;
     }
@@ -130,10 +125,8 @@ __global__ void __launch_bounds__(kSnThreads) sn_scale_pack_kernel(float* __rest
         const int r = i % kSnRows, c = cb + i / kSnRows;
         if (r < nr && c < L.cout) {
           const int row = r0 + r, tap = row / L.cin, ci = row - tap * L.cin;
-          const float v = tile[r][i / kSnRows], hi = round_tf32(v);
-          const int64_t o = (int64_t)c * K + (int64_t)tap * L.cin_pad + ci;
-          pack[L.tr_off + o] = hi;
-          if (pack_lo) pack[L.tr_off + plane + o] = round_tf32(v - hi);
+          const float v = tile[r][i / kSnRows];
+          pack[L.tr_off + (int64_t)c * K + (int64_t)tap * L.cin_pad + ci] = pack_exact ? v : round_tf32(v);
         }
       }
     }
@@ -147,10 +140,10 @@ using namespace nvae;
 
 extern "C" int nvae_spectral_norm(float* params, float* state, float* pack, const NvaeSnLayer* layers_dev,
                                   int n_layers, const int32_t* chunk_layer_dev, int n_chunks_total, int power_iter,
-                                  int pack_lo, float* sigma_out, float* ws, nvae_stream_t stream) {
+                                  int pack_exact, float* sigma_out, float* ws, nvae_stream_t stream) {
   if (n_layers <= 0 || n_chunks_total <= 0) return NVAE_E_BADSHAPE;
   if (!params || !layers_dev || !chunk_layer_dev) return NVAE_E_NULLPTR;
-  if (pack_lo && pack == nullptr) return NVAE_E_NULLPTR;
+  if (pack_exact && pack == nullptr) return NVAE_E_NULLPTR;
   if (power_iter) {
     if (!state || !sigma_out || !ws) return NVAE_E_NULLPTR;
     sn_wu_kernel<<<n_chunks_total, kSnThreads, 0, stream>>>(params, state, layers_dev, chunk_layer_dev, ws);
@@ -162,7 +155,7 @@ extern "C" int nvae_spectral_norm(float* params, float* state, float* pack, cons
   }
   if (power_iter || pack != nullptr) {
     sn_scale_pack_kernel<<<n_chunks_total, kSnThreads, 0, stream>>>(params, pack, layers_dev, chunk_layer_dev,
-                                                                   sigma_out, power_iter, pack_lo);
+                                                                   sigma_out, power_iter, pack_exact);
     NVAE_RETURN_IF_LAUNCH_FAILED();
   }
   return NVAE_OK;

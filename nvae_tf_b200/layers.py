@@ -56,8 +56,11 @@ class Conv2D(Layer):
         return self.rt.pack[self.tr_off:].data_ptr() if self.tr_off >= 0 else None
 
     def packed_dgrad(self):
-        """HWIO TF32 copy: the K-major B operand of the backward-data GEMM (None in fp32 mode)."""
-        return self.rt.pack[self.rnd_off:].data_ptr() if self.rnd_off >= 0 else None
+        """HWIO operand of the backward-data GEMM (K-major along Cout): the TF32-rounded copy in NVAE_PREC_TF32,
+        the master kernel itself in NVAE_PREC_TF32X3, None in fp32 mode."""
+        if self.rnd_off >= 0:
+            return self.rt.pack[self.rnd_off:].data_ptr()
+        return self.kernel.ptr() if self.tr_off >= 0 else None
 
     def __call__(self, x: DeviceTensor, x2=None, residual=None, **kw) -> DeviceTensor:
         if self.sn is None and self.tr_off >= 0 and not self.rt.sn_done:

@@ -99,7 +99,7 @@ class Runtime:
         else:
             self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
         self.precision = precision = _lib.default_precision() if precision is None else precision
-        self.pack_lo = int(precision == _lib.NVAE_PREC_TF32X3)
+        self.pack_exact = int(precision == _lib.NVAE_PREC_TF32X3)
         # which tensor-core conv operands get an explicit RN-to-TF32 pass when their producer did not round them
         self.tf32_round = os.environ.get("NVAE_TF32_ROUND", "dy")  # none | dy | all
         self.rng = np.random.default_rng(seed)
@@ -293,16 +293,20 @@ class Runtime:
 
     # ---- TF32 operand copies of the conv kernels (tensor-core modes) -----------------------------------
     def _alloc_packs(self) -> None:
-        """Two TF32-rounded copies per Conv2D kernel: HWIO (dgrad B operand) and [Cout][tap][Cin] (forward B
-        operand).  They are rewritten by nvae_spectral_norm's last pass whenever the weights change."""
+        """Two operand copies per Conv2D kernel: HWIO (dgrad B operand) and [Cout][tap][Cin] (forward B operand),
+        TF32-rounded in NVAE_PREC_TF32 and exact in NVAE_PREC_TF32X3.  They are rewritten by nvae_spectral_norm's
+        last pass whenever the weights change."""
         if self.precision == _lib.NVAE_PREC_FP32 or not self.convs:
             return
         off = 0
-        planes = 2 if self.precision == _lib.NVAE_PREC_TF32X3 else 1  # 3xTF32: value plane + low-order plane
         for conv in self.convs:
             n = (conv.kernel.size + 3) // 4 * 4
-            conv.rnd_off, conv.tr_off = off, off + planes * n
-            off += 2 * planes * n
+            if self.pack_exact:  # 3xTF32: the HWIO master kernel itself is the dgrad operand
+                conv.rnd_off, conv.tr_off = -1, off
+                off += n
+            else:
+                conv.rnd_off, conv.tr_off = off, off + n
+                off += 2 * n
         self.pack = torch.zeros(max(off, 4), device=self.device)
         self._plain_tables: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
 
@@ -334,7 +338,7 @@ class Runtime:
             self._plain_tables[key] = (dev, cl)
         dev, cl = self._plain_tables[key]
         self.lib.spectral_norm(self.params.data_ptr(), self.state.data_ptr(), self.pack.data_ptr(), dev.data_ptr(), 1,
-                               cl.data_ptr(), cl.numel(), 0, self.pack_lo, None, None, self.stream)
+                               cl.data_ptr(), cl.numel(), 0, self.pack_exact, None, None, self.stream)
 
     # ---- spectral normalisation tables -------------------------------------------------
     def _build_sn_tables(self) -> None:
@@ -369,7 +373,7 @@ class Runtime:
             return
         self.lib.spectral_norm(self.params.data_ptr(), self.state.data_ptr(), self._pack_ptr(),
                                self.sn_layers_dev.data_ptr(), self.sn_n, self.sn_chunk_layer.data_ptr(),
-                               self.sn_chunk_layer.numel(), int(power_iter), self.pack_lo, self.sn_sigma.data_ptr(),
+                               self.sn_chunk_layer.numel(), int(power_iter), self.pack_exact, self.sn_sigma.data_ptr(),
                                self.sn_ws.data_ptr(), self.stream)
 
     @contextmanager
@@ -397,7 +401,7 @@ class Runtime:
             self._sn_single[index] = (dev, cl)
         dev, cl = self._sn_single[index]
         self.lib.spectral_norm(self.params.data_ptr(), self.state.data_ptr(), self._pack_ptr(), dev.data_ptr(), 1,
-                               cl.data_ptr(), cl.numel(), int(power_iter), self.pack_lo,
+                               cl.data_ptr(), cl.numel(), int(power_iter), self.pack_exact,
                                self.sn_sigma[index:].data_ptr(),
                                self.sn_ws.data_ptr(), self.stream)
 
@@ -449,7 +453,7 @@ def bn_act(rt: Runtime, x: DeviceTensor, bn, act: int, training: bool, upsample:
     up = (H, W) if upsample else (0, 0)
     out = rt.empty(N, 2 * H, 2 * W, Cc) if upsample else rt.empty(N, H, W, Cc)
     rt.lib.bn_act_fwd(x.ptr(), _rows(x.data), Cc, stat.data_ptr() if stat is not None else None, act, up[0], up[1],
-                      int(rt.precision == _lib.NVAE_PREC_TF32), out.data_ptr(), None, rt.stream)
+                      int(rt.precision == _lib.NVAE_PREC_TF32), out.data_ptr(), rt.stream)
     y = DeviceTensor(out, x.needs_grad or bn is not None)
     if rt.tape is not None:
         def bwd():
@@ -490,8 +494,8 @@ def conv2d(rt: Runtime, x: DeviceTensor, conv, x2: Optional[DeviceTensor] = None
     y = out if out is not None else DeviceTensor(rt.empty(d.N, d.Ho, d.Wo, d.Cout))
     ws, wsb = rt.workspace(rt.lib._nvae_conv2d_ws_bytes(C.byref(d), 0))
     bias = conv.bias
-    # single-pass TF32 only: operands whose producer did not round them get an explicit RN pass (3xTF32 keeps
-    # the low-order bits in a second plane instead, computed inside the conv entry points)
+    # single-pass TF32 only: operands whose producer did not round them get an explicit RN pass (3xTF32 splits
+    # the raw fp32 tiles into high and low parts inside the convolution kernel)
     tc = [bool(rt.lib._nvae_conv2d_uses_tensor_cores(C.byref(d), i)) for i in range(3)] \
         if rt.precision == _lib.NVAE_PREC_TF32 else [False] * 3
     if rt.tf32_round == "all" and (tc[0] or tc[2]):

@@ -1,0 +1,133 @@
+// Development probe (not product code): tcgen05.mma kind::tf32 issue throughput from shared-memory operands
+// as a function of N and operand major-ness.  One CTA per SM, operands are whatever the shared memory holds
+// (zero-initialised), NITER back-to-back MMAs into one TMEM accumulator, timed with clock64.
+//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/mma_probe tools/mma_probe.cu
+//   run  : tools/mma_probe
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint64_t layout) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (layout << 61);
+}
+__device__ __forceinline__ uint32_t idesc_tf32(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// mode 0: tf32 K-major SW128; 1: tf32 MN-major; 2: bf16 K-major SW128; 3: tf32 K-major SW32; 4: tf32 K-major SW64
+// hammer: warps 1..3 stream float4 read-modify-writes over a separate 32 KB region while the MMAs run
+__global__ void __launch_bounds__(128, 1) probe(int N, int mode, int niter, int hammer, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  __shared__ volatile int done;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0;
+  if (threadIdx.x == 0) {
+    done = 0;
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base;
+  long long t0 = 0, t1 = 0;
+  if (threadIdx.x == 0) {
+    const uint32_t sa = base, sb = base + 16384;
+    uint64_t da, db;
+    uint32_t idesc;
+    if (mode == 1) {
+      da = desc_sw128(sa, 4096, 512, 1); db = desc_sw128(sb, 4096, 512, 1);
+      idesc = idesc_tf32(128, N, 1, 1);
+    } else if (mode == 3) {
+      da = desc_sw128(sa, 16, 256, 6); db = desc_sw128(sb, 16, 256, 6);
+      idesc = idesc_tf32(128, N, 0, 0);
+    } else if (mode == 4) {
+      da = desc_sw128(sa, 16, 512, 4); db = desc_sw128(sb, 16, 512, 4);
+      idesc = idesc_tf32(128, N, 0, 0);
+    } else {
+      da = desc_sw128(sa, 16, 1024, 2); db = desc_sw128(sb, 16, 1024, 2);
+      idesc = mode == 2 ? idesc_bf16(128, N) : idesc_tf32(128, N, 0, 0);
+    }
+    t0 = clock64();
+    for (int it = 0; it < niter; ++it) {
+      const uint64_t k = (uint64_t)(2 * (it & 3));
+      if (mode == 2) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem), "l"(da + k), "l"(db + k), "r"(idesc), "r"(it) : "memory");
+      } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem), "l"(da + (mode == 0 ? k : mode == 4 ? (k & 2) : 0)), "l"(db + (mode == 0 ? k : mode == 4 ? (k & 2) : 0)), "r"(idesc), "r"(it) : "memory");
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    while (!mbar_try_wait(smem_u32(&bar), 0)) {}
+    t1 = clock64();
+    done = 1;
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  } else if (hammer && threadIdx.x >= 32) {
+    float4* reg = reinterpret_cast<float4*>(smem_raw + 1024 + 16384 + 32768);  // 32 KB scratch after A and B
+    const int t = threadIdx.x - 32;
+    float4 acc = make_float4(0, 0, 0, 0);
+    while (!done) {
+#pragma unroll 4
+      for (int i = t; i < 1024; i += 96) {
+        float4 v = reg[i];
+        v.x += 1.f; acc.x += v.y;
+        reg[i + 1024] = v;
+      }
+    }
+    if (acc.x == 123.f) out[1] = 1;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  }
+}
+
+int main() {
+  long long* d;
+  cudaMalloc(&d, 16);
+  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  const int niter = 4096;
+  const char* names[5] = {"tf32 K-major SW128", "tf32 MN-major     ", "bf16 K-major SW128", "tf32 K-major SW32 ", "tf32 K-major SW64 "};
+  for (int mode = 0; mode < 5; ++mode)
+    for (int N : {64, 128, 192, 256}) {
+      for (int hammer : {0, 1}) {
+        const int grid = 148;
+        probe<<<grid, 128, 100 * 1024>>>(N, mode, niter, hammer, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long cyc = 0;
+        cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+        const double per = (double)cyc / niter;
+        const int K = mode == 2 ? 16 : 8;
+        printf("%s N=%3d hammer=%d: %7.1f cyc/MMA  %6.0f MAC/cyc/SM  (ideal %d cyc)  %s\n", names[mode], N, hammer, per,
+               128.0 * N * K / per, N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
+      }
+    }
+  return 0;
+}
