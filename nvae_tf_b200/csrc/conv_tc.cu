@@ -24,8 +24,8 @@
 // that covers only part of a tile's K range writes its raw accumulator to a partial buffer and a fix-up
 // kernel sums the partials of each split tile in CTA order (deterministic) and applies the epilogue.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..9 = lo-part converters during the main loop, then epilogue (tcgen05.ld -> bias / residual /
-// accumulate -> 128-bit stores).
+// warps 2..9 = lo-part converters, warps 10..13 = epilogue (tcgen05.ld -> bias / residual / accumulate ->
+// 128-bit stores) on a double-buffered TMEM accumulator, so the next tile's MMAs overlap the drain.
 #include <cuda.h>
 
 #include "conv_internal.h"
@@ -37,8 +37,9 @@ namespace {
 constexpr int kBM = 128;         // UMMA M (TMEM lanes)
 constexpr int kChunk = 32;       // fp32 elements per 128-byte swizzle row
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 320;    // 10 warps: TMA, MMA, 8 x converter/epilogue
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 256;                   // warps 2..9: lo-part converters (3xTF32)
+constexpr int kEpiThreads = 128;                    // warps 10..13: epilogue, one per TMEM lane group
+constexpr int kThreads = 64 + kConvThreads + kEpiThreads;
 constexpr int kSmemBudget = 220 * 1024;
 
 // ------------------------------------------------------------------------------------------------
@@ -142,8 +143,8 @@ struct SmemCtl {
   uint64_t empty[kMaxStages];
   uint64_t conv[kMaxStages];      // lo slot filled by the converters
   uint64_t lo_empty[kMaxStages];  // lo slot consumed by the MMAs
-  uint64_t acc_full;
-  uint64_t acc_empty;
+  uint64_t acc_full[2];           // TMEM accumulator double buffer: MMAs of segment i+1 overlap the epilogue of i
+  uint64_t acc_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -295,14 +296,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(smem_u32(&ctl->conv[i]), kConvThreads / 32);
       mbar_init(smem_u32(&ctl->lo_empty[i]), 1);
     }
-    mbar_init(smem_u32(&ctl->acc_full), 1);
-    mbar_init(smem_u32(&ctl->acc_empty), kConvThreads / 32);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&ctl->acc_full[i]), 1);
+      mbar_init(smem_u32(&ctl->acc_empty[i]), kEpiThreads / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tma_prefetch_desc(&maps.m[0]);
     tma_prefetch_desc(&maps.m[2]);
   }
-  if (warp == 1) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols_for(p.BN));
+  if (warp == 1) tmem_alloc(smem_u32(&ctl->tmem_base), 2u * tmem_cols_for(p.BN));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -387,7 +390,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (long long u = u_begin; u < u_end; ++seg) {
         const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
         const int kb = (int)min((long long)p.KU, ka + (u_end - u));
-        mbar_wait(smem_u32(&ctl->acc_empty), ((uint32_t)seg & 1u) ^ 1u);
+        const uint32_t acc = tmem + (uint32_t)(seg & 1) * tmem_cols_for(p.BN);
+        mbar_wait(smem_u32(&ctl->acc_empty[seg & 1]), (((uint32_t)seg >> 1) & 1u) ^ 1u);
         tc_fence_after();
         for (int k = ka; k < kb; ++k, ++it) {
           const int st = it % p.stages;
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           // high parts first: they need nothing from the converters, which work on this stage meanwhile
           for (int j = 0; j < ksteps; ++j)
-            umma_tf32(tmem, da + kadv * j, db + kadv * j, idesc, (k > ka || j > 0) ? 1u : 0u);
+            umma_tf32(acc, da + kadv * j, db + kadv * j, idesc, (k > ka || j > 0) ? 1u : 0u);
           if (p.passes == 3) {
             const int ls = it % p.lo_stages;
             mbar_wait(smem_u32(&ctl->conv[ls]), (uint32_t)(it / p.lo_stages) & 1u);
@@ -421,63 +425,63 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               la = umma_desc_sw128(sl, 16, 1024);
               lb = umma_desc_sw128(sl + p.a_bytes, 16, 1024);
             }
-            for (int j = 0; j < ksteps; ++j) umma_tf32(tmem, da + kadv * j, lb + kadv * j, idesc, 1u);
-            for (int j = 0; j < ksteps; ++j) umma_tf32(tmem, la + kadv * j, db + kadv * j, idesc, 1u);
+            for (int j = 0; j < ksteps; ++j) umma_tf32(acc, da + kadv * j, lb + kadv * j, idesc, 1u);
+            for (int j = 0; j < ksteps; ++j) umma_tf32(acc, la + kadv * j, db + kadv * j, idesc, 1u);
             umma_commit(smem_u32(&ctl->lo_empty[ls]));
           }
           umma_commit(smem_u32(&ctl->empty[st]));
         }
-        umma_commit(smem_u32(&ctl->acc_full));
+        umma_commit(smem_u32(&ctl->acc_full[seg & 1]));
         u += kb - ka;
       }
     }
+  } else if (warp < 2 + kConvThreads / 32) {
+    // ---------------- converters (3xTF32): lo = v - trunc_tf32(v) of every staged tile ----------------
+    if (p.passes == 3) {
+      const int ct = (warp - 2) * 32 + lane;
+      const int n16 = (int)(raw_bytes >> 4);
+      const int n_units = (int)(u_end - u_begin);
+      for (int it = 0; it < n_units; ++it) {
+        const int st = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        const int ls = it % p.lo_stages;
+        mbar_wait(smem_u32(&ctl->lo_empty[ls]), ((uint32_t)(it / p.lo_stages) & 1u) ^ 1u);
+        mbar_wait(smem_u32(&ctl->full[st]), ph);
+        const float4* src = reinterpret_cast<const float4*>(smem_raw + (stage_base - smem_u32(smem_raw)) +
+                                                            (size_t)st * stage_bytes);
+        float4* dst = reinterpret_cast<float4*>(smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)ls * raw_bytes);
+        int i = ct;
+        for (; i + 3 * kConvThreads < n16; i += 4 * kConvThreads) {  // loads first: 4 independent LDS.128 in flight
+          const float4 v0 = src[i], v1 = src[i + kConvThreads], v2 = src[i + 2 * kConvThreads],
+                       v3 = src[i + 3 * kConvThreads];
+          dst[i] = tf32_lo4(v0);
+          dst[i + kConvThreads] = tf32_lo4(v1);
+          dst[i + 2 * kConvThreads] = tf32_lo4(v2);
+          dst[i + 3 * kConvThreads] = tf32_lo4(v3);
+        }
+        for (; i < n16; i += kConvThreads) dst[i] = tf32_lo4(src[i]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&ctl->conv[ls]));
+      }
+    }
   } else {
-    // ---------------- converters (3xTF32) + epilogue ----------------
-    const int lg = warp & 3;           // TMEM lane group this warp may read: lanes [32*lg, +32)
-    const int chalf = (warp - 2) >> 2;  // two warps share a lane group: even / odd 32-column blocks
-    const int ct = (warp - 2) * 32 + lane;
+    // ---------------- epilogue: TMEM -> registers -> global (final tile or raw partial) ----------------
+    const int lg = warp & 3;  // TMEM lane group this warp may read: lanes [32*lg, +32)
     const int row = lg * 32 + lane;
-    int it = 0, seg = 0;
+    int seg = 0;
     for (long long u = u_begin; u < u_end; ++seg) {
       const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
       const int kb = (int)min((long long)p.KU, ka + (u_end - u));
       const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
-      if (p.passes == 3) {
-        const int n16 = (int)(raw_bytes >> 4);
-        for (int k = ka; k < kb; ++k, ++it) {
-          const int st = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          const int ls = it % p.lo_stages;
-          mbar_wait(smem_u32(&ctl->lo_empty[ls]), ((uint32_t)(it / p.lo_stages) & 1u) ^ 1u);
-          mbar_wait(smem_u32(&ctl->full[st]), ph);
-          const float4* src = reinterpret_cast<const float4*>(smem_raw + (stage_base - smem_u32(smem_raw)) +
-                                                              (size_t)st * stage_bytes);
-          float4* dst = reinterpret_cast<float4*>(smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)ls * raw_bytes);
-          int i = ct;
-          for (; i + 3 * kConvThreads < n16; i += 4 * kConvThreads) {  // loads first: 4 independent LDS.128 in flight
-            const float4 v0 = src[i], v1 = src[i + kConvThreads], v2 = src[i + 2 * kConvThreads],
-                         v3 = src[i + 3 * kConvThreads];
-            dst[i] = tf32_lo4(v0);
-            dst[i + kConvThreads] = tf32_lo4(v1);
-            dst[i + 2 * kConvThreads] = tf32_lo4(v2);
-            dst[i + 3 * kConvThreads] = tf32_lo4(v3);
-          }
-          for (; i < n16; i += kConvThreads) dst[i] = tf32_lo4(src[i]);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&ctl->conv[ls]));
-        }
-      } else {
-        it += kb - ka;
-      }
-      mbar_wait(smem_u32(&ctl->acc_full), (uint32_t)seg & 1u);
+      const uint32_t acc = tmem + (uint32_t)(seg & 1) * tmem_cols_for(p.BN) + ((uint32_t)(lg * 32) << 16);
+      mbar_wait(smem_u32(&ctl->acc_full[seg & 1]), ((uint32_t)seg >> 1) & 1u);
       tc_fence_after();
-      const bool full_tile = ka == 0 && kb == p.KU;
-      if (full_tile) {
+      if (ka == 0 && kb == p.KU) {
         const RowCtx rc = row_ctx<WGRAD>(p, mt, row);
-        for (int j = chalf * 32; j < p.BN; j += 64) {
+        for (int j = 0; j < p.BN; j += 32) {
           uint32_t v[32];
-          tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)j, v);
+          tmem_ld32(acc + (uint32_t)j, v);
 #pragma unroll
           for (int q = 0; q < 32; q += 4)
             store4<WGRAD>(p, rc, nt, j + q,
@@ -487,9 +491,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       } else {
         // slot 0: continues a tile begun by an earlier CTA; slot 1: begins a tile a later CTA finishes
         float* dst = p.part + (((int64_t)cta * 2 + (ka > 0 ? 0 : 1)) * kBM + row) * p.BN;
-        for (int j = chalf * 32; j < p.BN; j += 64) {
+        for (int j = 0; j < p.BN; j += 32) {
           uint32_t v[32];
-          tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)j, v);
+          tmem_ld32(acc + (uint32_t)j, v);
 #pragma unroll
           for (int q = 0; q < 32; q += 4)
             if (j + q < p.BN)
@@ -499,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty));
+      if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty[seg & 1]));
       u += kb - ka;
     }
   }
@@ -507,12 +511,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, tmem_cols_for(p.BN));
+    tmem_dealloc(tmem, 2u * tmem_cols_for(p.BN));
   }
 }
 
 // Fix-up: block (c, y) finishes the tile whose K range ENDS inside CTA c's first segment: sums the partials of
-// the CTAs that covered it, in CTA order, and applies the epilogue.  16 tile rows per blockIdx.y.
+// the CTAs that covered it, in CTA order, and applies the epilogue.  kFixRows tile rows per blockIdx.y.
+constexpr int kFixRows = 4;
 template <bool WGRAD>
 __global__ void __launch_bounds__(256) conv_tc_fixup_kernel(const TcParams p, int G) {
   const int c = blockIdx.x;
@@ -524,11 +529,21 @@ __global__ void __launch_bounds__(256) conv_tc_fixup_kernel(const TcParams p, in
   const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
   const int bn4 = p.BN / 4;
   const int64_t slot = (int64_t)kBM * p.BN;
-  for (int i = threadIdx.x; i < 16 * bn4; i += blockDim.x) {
-    const int row = blockIdx.y * 16 + i / bn4, col = (i % bn4) * 4;
+  for (int i = threadIdx.x; i < kFixRows * bn4; i += blockDim.x) {
+    const int row = blockIdx.y * kFixRows + i / bn4, col = (i % bn4) * 4;
     const int64_t o = (int64_t)row * p.BN + col;
     float4 s = ldg4(p.part + ((int64_t)cf * 2 + 1) * slot + o);
-    for (int k = cf + 1; k <= c; ++k) {
+    int k = cf + 1;
+    for (; k + 3 <= c; k += 4) {  // four independent loads in flight; the additions keep CTA order
+      const float4 v0 = ldg4(p.part + ((int64_t)k * 2) * slot + o), v1 = ldg4(p.part + ((int64_t)(k + 1) * 2) * slot + o),
+                   v2 = ldg4(p.part + ((int64_t)(k + 2) * 2) * slot + o),
+                   v3 = ldg4(p.part + ((int64_t)(k + 3) * 2) * slot + o);
+      s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
+      s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
+      s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
+      s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
+    }
+    for (; k <= c; ++k) {
       const float4 v = ldg4(p.part + ((int64_t)k * 2) * slot + o);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
@@ -732,7 +747,7 @@ int launch(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t 
   conv_tc_kernel<WGRAD><<<pl.G, kThreads, pl.smem, stream>>>(maps, p);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   if (pl.split) {
-    conv_tc_fixup_kernel<WGRAD><<<dim3(pl.G, kBM / 16), 256, 0, stream>>>(p, pl.G);
+    conv_tc_fixup_kernel<WGRAD><<<dim3(pl.G, kBM / kFixRows), 256, 0, stream>>>(p, pl.G);
     NVAE_RETURN_IF_LAUNCH_FAILED();
   }
   return NVAE_OK;
