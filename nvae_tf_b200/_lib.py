@@ -13,7 +13,7 @@ from typing import Dict, List, Tuple
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "nvae_b200.h")
-LIB_PATH = os.path.join(_HERE, "libnvae_b200.so")
+LIB_PATH = os.environ.get("NVAE_LIB") or os.path.join(_HERE, "libnvae_b200.so")  # NVAE_LIB: development builds
 
 NVAE_ACT_NONE, NVAE_ACT_SWISH, NVAE_ACT_ELU = 0, 1, 2
 NVAE_PREC_FP32, NVAE_PREC_TF32, NVAE_PREC_TF32X3 = 0, 1, 2

@@ -40,7 +40,7 @@ constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 256;                   // warps 2..9: lo-part converters (3xTF32)
 constexpr int kEpiThreads = 128;                    // warps 10..13: epilogue, one per TMEM lane group
 constexpr int kThreads = 64 + kConvThreads + kEpiThreads;
-constexpr int kSmemBudget = 220 * 1024;
+constexpr int kSmemBudget = 208 * 1024;  // operand rings; the epilogue staging (17 KB) and barriers come on top
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -138,6 +138,23 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int n, int a_mn_major, int b
 }
 
 
+#ifdef NVAE_TC_TIMING
+// development build only: per-CTA timestamps (ns, %globaltimer) [start, setup done, first tile landed, last MMA
+// issued, accumulator complete, epilogue done, exit]
+__device__ unsigned long long g_tc_timing[148 * 8];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(i) g_tc_timing[blockIdx.x * 8 + (i)] = gtime()
+extern "C" __attribute__((visibility("default"))) int nvae_debug_tc_timing(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_tc_timing, sizeof(g_tc_timing));
+}
+#else
+#define TC_STAMP(i)
+#endif
+
 struct SmemCtl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
@@ -147,6 +164,14 @@ struct SmemCtl {
   uint64_t acc_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
+};
+
+// Epilogue staging: each epilogue warp transposes its 32 rows x 32 columns through shared memory (16-byte slots,
+// XOR-swizzled by row so both the row-per-lane writes and the 8-lanes-per-row reads are conflict-free) so that
+// global stores are 128-byte row segments instead of 32 scattered 16-byte pieces.
+struct EpiSmem {
+  float4 tile[4][32][8];
+  long long rowbase[kBM];  // RowCtx.base of each tile row, -1 when the row is not stored
 };
 
 __device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
@@ -169,6 +194,8 @@ struct TcParams {
   int BN, stages, lo_stages, passes;  // raw-tile ring, lo-tile ring (3xTF32 only); passes: 1 = TF32, 3 = 3xTF32
   int n_ntiles;                 // tile t = mt * n_ntiles + nt
   int KU;                       // k-units (pipeline stages) per tile
+  int T;                        // tiles
+  int whole_tiles;              // 1: CTA ranges are whole tiles (no tile is split); 0: equal unit ranges (stream-K)
   long long U;                  // tiles * KU
   uint32_t a_bytes, b_bytes;    // raw bytes of the A / B part of one stage
   float* part;                  // [gridDim.x][2][128][BN] raw partial accumulators
@@ -192,7 +219,9 @@ struct TcParams {
 };
 
 // ---- stream-K partition (identical arithmetic in every role and in the fix-up kernel) -----------------
-__device__ __forceinline__ long long cta_u0(const TcParams& p, int c, int G) { return (long long)c * p.U / G; }
+__device__ __forceinline__ long long cta_u0(const TcParams& p, int c, int G) {
+  return p.whole_tiles ? ((long long)c * p.T / G) * p.KU : (long long)c * p.U / G;
+}
 // first CTA whose range reaches into tile t
 __device__ __forceinline__ int first_cta_of(const TcParams& p, int t, int G) {
   const long long x = (long long)t * p.KU;
@@ -288,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int nch = p.nchunk1 + p.nchunk2;
 
   if (threadIdx.x == 0) {
+    TC_STAMP(0);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(smem_u32(&ctl->full[i]), 1);
       mbar_init(smem_u32(&ctl->empty[i]), 1);
@@ -310,6 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ctl->tmem_base;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -398,6 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           mbar_wait(smem_u32(&ctl->full[st]), ph);
           tc_fence_after();
+          if (it == 0) TC_STAMP(2);
           const uint32_t sa = stage_base + (uint32_t)st * stage_bytes;
           uint64_t da, db;
           if (WGRAD) {
@@ -432,6 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           umma_commit(smem_u32(&ctl->empty[st]));
         }
         umma_commit(smem_u32(&ctl->acc_full[seg & 1]));
+        TC_STAMP(3);
         u += kb - ka;
       }
     }
@@ -466,44 +499,55 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else {
-    // ---------------- epilogue: TMEM -> registers -> global (final tile or raw partial) ----------------
+    // ---------------- epilogue: TMEM -> registers -> smem transpose -> global (final tile or raw partial) ----
     const int lg = warp & 3;  // TMEM lane group this warp may read: lanes [32*lg, +32)
     const int row = lg * 32 + lane;
+    EpiSmem* epi = reinterpret_cast<EpiSmem*>(smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)p.lo_stages * raw_bytes);
+    const int q = lane & 7, r0 = lane >> 3;
     int seg = 0;
     for (long long u = u_begin; u < u_end; ++seg) {
       const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
       const int kb = (int)min((long long)p.KU, ka + (u_end - u));
       const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
+      const bool full_tile = ka == 0 && kb == p.KU;
+      {
+        const RowCtx rc = row_ctx<WGRAD>(p, mt, row);
+        epi->rowbase[row] = (rc.ok || !full_tile) ? rc.base : -1;
+      }
+      // slot 0: continues a tile begun by an earlier CTA; slot 1: begins a tile a later CTA finishes
+      float* pdst = p.part + (((int64_t)cta * 2 + (ka > 0 ? 0 : 1)) * kBM + lg * 32) * p.BN;
       const uint32_t acc = tmem + (uint32_t)(seg & 1) * tmem_cols_for(p.BN) + ((uint32_t)(lg * 32) << 16);
       mbar_wait(smem_u32(&ctl->acc_full[seg & 1]), ((uint32_t)seg >> 1) & 1u);
       tc_fence_after();
-      if (ka == 0 && kb == p.KU) {
-        const RowCtx rc = row_ctx<WGRAD>(p, mt, row);
-        for (int j = 0; j < p.BN; j += 32) {
-          uint32_t v[32];
-          tmem_ld32(acc + (uint32_t)j, v);
+      if (threadIdx.x == kThreads - 1) TC_STAMP(4);
+      for (int j = 0; j < p.BN; j += 32) {
+        uint32_t v[32];
+        tmem_ld32(acc + (uint32_t)j, v);
 #pragma unroll
-          for (int q = 0; q < 32; q += 4)
-            store4<WGRAD>(p, rc, nt, j + q,
-                          make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]),
-                                      __uint_as_float(v[q + 3])));
-        }
-      } else {
-        // slot 0: continues a tile begun by an earlier CTA; slot 1: begins a tile a later CTA finishes
-        float* dst = p.part + (((int64_t)cta * 2 + (ka > 0 ? 0 : 1)) * kBM + row) * p.BN;
-        for (int j = 0; j < p.BN; j += 32) {
-          uint32_t v[32];
-          tmem_ld32(acc + (uint32_t)j, v);
+        for (int s4 = 0; s4 < 8; ++s4)
+          epi->tile[lg][lane][s4 ^ (lane & 7)] = make_float4(__uint_as_float(v[4 * s4]), __uint_as_float(v[4 * s4 + 1]),
+                                                             __uint_as_float(v[4 * s4 + 2]), __uint_as_float(v[4 * s4 + 3]));
+        __syncwarp();
 #pragma unroll
-          for (int q = 0; q < 32; q += 4)
-            if (j + q < p.BN)
-              stg4(dst + j + q, make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]),
-                                            __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3])));
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 4 * i;
+          const float4 o = epi->tile[lg][r][q ^ (r & 7)];
+          const int col = j + 4 * q;
+          if (full_tile) {
+            RowCtx rc;
+            rc.base = epi->rowbase[lg * 32 + r];
+            rc.ok = rc.base >= 0;
+            store4<WGRAD>(p, rc, nt, col, o);
+          } else if (col < p.BN) {
+            stg4(pdst + (int64_t)r * p.BN + col, o);
+          }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty[seg & 1]));
+      if (threadIdx.x == kThreads - 1) TC_STAMP(5);
       u += kb - ka;
     }
   }
@@ -512,6 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 2u * tmem_cols_for(p.BN));
+    if (lane == 0) TC_STAMP(6);
   }
 }
 
@@ -632,9 +677,10 @@ bool pick_pix_tile(int N, int H, int W, int max_rows, int row_mult, PixTile* t) 
   return true;
 }
 
-// widest N tile <= 256 that cuts n_total into equal parts (wide MMAs run closest to the tensor-pipe peak)
-int pick_bn(int n_total, int mult) {
-  const int nt = (n_total + 255) / 256;
+// widest N tile <= cap that cuts n_total into equal parts (wide MMAs run closest to the tensor-pipe peak).
+// cap: 256 in TF32; 192 in 3xTF32, where (128 + BN) x 128 B tiles must fit five times (3 raw + 2 lo slots).
+int pick_bn(int n_total, int mult, int cap) {
+  const int nt = (n_total + cap - 1) / cap;
   return (int)round_up(ceil_div(n_total, nt), mult);
 }
 
@@ -657,13 +703,16 @@ struct Plan {
   int BN, stages, lo_stages, n_mtiles, n_ntiles, KU, G, njobs;
   uint32_t a_bytes, b_bytes;
   long long U;
+  int whole_tiles;
   bool split;          // some tile is shared between CTAs -> partial buffer + fix-up launch
   size_t part_bytes;
   size_t smem;
 };
 
-constexpr int kMinUnitsPerCta = 4;
-
+// Work partition.  Splitting a tile's K range over several CTAs costs a partial-accumulator round trip and the
+// fix-up launch, so it is done only when the main loop it shortens is longer than that (small spatial scales:
+// 18-72 tiles, K up to 2304).  Times in microseconds, calibrated on B200 (one 32-deep K stage ~ 0.95 us in
+// 3xTF32, 0.35 us in TF32; fix-up ~ 5 us + partial traffic at ~3 TB/s).
 bool finish_plan(Plan* pl, int passes) {
   const size_t raw = (size_t)pl->a_bytes + pl->b_bytes;
   int slots = (int)((kSmemBudget - 2048) / raw);
@@ -677,14 +726,24 @@ bool finish_plan(Plan* pl, int passes) {
     pl->stages = slots;
   }
   if (pl->stages > kMaxStages) pl->stages = kMaxStages;
-  pl->smem = sizeof(SmemCtl) + 1024 + (size_t)(pl->stages + pl->lo_stages) * raw;
-  pl->U = (long long)pl->n_mtiles * pl->n_ntiles * pl->KU;
-  long long g = pl->U / kMinUnitsPerCta;
-  if (g > kNumSMs) g = kNumSMs;
-  if (g < 1) g = 1;
-  pl->G = (int)g;
-  pl->split = false;
-  for (int c = 1; c < pl->G && !pl->split; ++c) pl->split = ((long long)c * pl->U / pl->G) % pl->KU != 0;
+  pl->smem = sizeof(SmemCtl) + 1024 + (size_t)(pl->stages + pl->lo_stages) * raw + sizeof(EpiSmem);
+  const long long T = (long long)pl->n_mtiles * pl->n_ntiles;
+  pl->U = T * pl->KU;
+  const double t_unit = passes == 3 ? 0.95 : 0.35;
+  const double slot_us = (double)kBM * pl->BN * 4 * 2 / 3.0e6;  // one partial written + read back
+  pl->whole_tiles = 1;
+  pl->G = (int)(T < kNumSMs ? T : kNumSMs);
+  double best = (double)ceil_div(T, pl->G) * pl->KU * t_unit;
+  if (T >= kNumSMs) {
+    const double sk = (double)pl->U / kNumSMs * t_unit + 5.0 + 2.0 * kNumSMs * slot_us;
+    if (sk < best) { pl->whole_tiles = 0; pl->G = kNumSMs; }
+  } else {
+    for (int S = 2; S * T <= kNumSMs && 2 * S <= pl->KU; ++S) {  // S CTAs per tile, >= 2 stages each
+      const double t = (double)ceil_div(pl->KU, S) * t_unit + 5.0 + (double)S * T * slot_us;
+      if (t < best) { best = t; pl->whole_tiles = 0; pl->G = (int)(S * T); }
+    }
+  }
+  pl->split = !pl->whole_tiles;
   pl->part_bytes = pl->split ? al256((size_t)pl->G * 2 * kBM * pl->BN * sizeof(float)) : 0;
   return true;
 }
@@ -695,7 +754,7 @@ bool plan_gemm(const NvaeConvDesc* d, int which, Plan* pl) {
   const int passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
   const int Ct = d->Cin + d->Cin2, taps = d->R * d->S;
   const int n_total = which == 0 ? d->Cout : Ct;
-  pl->BN = pick_bn(n_total, 16);
+  pl->BN = pick_bn(n_total, 16, passes == 3 ? 192 : 256);
   pl->n_mtiles = pl->t.n_tiles;
   pl->n_ntiles = (int)ceil_div(n_total, pl->BN);
   const int nch = which == 0 ? (int)(ceil_div(d->Cin, kChunk) + ceil_div(d->Cin2, kChunk)) : (int)ceil_div(d->Cout, kChunk);
@@ -716,7 +775,7 @@ bool plan_wgrad(const NvaeConvDesc* d, Plan* pl) {
   const int nch = (int)(ceil_div(d->Cin, kChunk) + ceil_div(d->Cin2, kChunk));
   pl->njobs = d->R * d->S * nch;
   pl->n_mtiles = (pl->njobs + 3) / 4;
-  pl->BN = pick_bn(d->Cout, 32);
+  pl->BN = pick_bn(d->Cout, 32, passes == 3 ? 192 : 256);
   // at least 3 raw + 2 lo (3xTF32) / 3 raw (TF32) slots in shared memory
   const size_t want = passes == 3 ? 5 : 3;
   while ((size_t)(4 + pl->BN / kChunk) * KP * 128 * want > (size_t)kSmemBudget - 2048 && pl->BN > 32) pl->BN -= 32;
@@ -732,6 +791,7 @@ void fill_common(TcParams* p, const NvaeConvDesc* d, const Plan& pl, float* part
   p->tw = pl.t.tw; p->th = pl.t.th; p->tn = pl.t.tn; p->tiles_h = pl.t.tiles_h;
   p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
   p->n_ntiles = pl.n_ntiles; p->KU = pl.KU; p->U = pl.U;
+  p->T = pl.n_mtiles * pl.n_ntiles; p->whole_tiles = pl.whole_tiles;
   p->a_bytes = pl.a_bytes; p->b_bytes = pl.b_bytes;
   p->part = part;
 }
@@ -740,7 +800,7 @@ template <bool WGRAD>
 int launch(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }

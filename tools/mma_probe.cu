@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int mode, int niter, int 
   __shared__ uint32_t tmem_base;
   __shared__ volatile int done;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0;
+  for (int i = threadIdx.x; i < 196 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0;
   if (threadIdx.x == 0) {
     done = 0;
     mbar_init(smem_u32(&bar), 1);
@@ -72,6 +72,22 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int mode, int niter, int 
       idesc = mode == 2 ? idesc_bf16(128, N) : idesc_tf32(128, N, 0, 0);
     }
     t0 = clock64();
+    if (mode == 5) {
+      // like the 3xTF32 main loop: 4 slots of (A 16 KB | B N*128 B) raw + lo copies, per k-unit 4 (hi,hi) + 4 (hi,lo) + 4 (lo,hi)
+      const uint32_t raw = 16384u + (uint32_t)N * 128u;
+      const uint32_t idesc5 = idesc_tf32(128, N, 0, 0);
+      for (int it = 0; it < niter / 12; ++it) {
+        const uint32_t s0 = base + (uint32_t)(it % 2) * 2u * raw;
+        const uint64_t a = desc_sw128(s0, 16, 1024, 2), b = desc_sw128(s0 + 16384, 16, 1024, 2);
+        const uint64_t lo = raw >> 4;
+        for (int pass = 0; pass < 3; ++pass)
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t aa = a + (pass == 2 ? lo : 0) + 2 * j, bb = b + (pass == 1 ? lo : 0) + 2 * j;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(tmem), "l"(aa), "l"(bb), "r"(idesc5), "r"(it + pass + j) : "memory");
+          }
+      }
+    } else
     for (int it = 0; it < niter; ++it) {
       const uint64_t k = (uint64_t)(2 * (it & 3));
       if (mode == 2) {
@@ -112,14 +128,14 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int mode, int niter, int 
 int main() {
   long long* d;
   cudaMalloc(&d, 16);
-  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  const int niter = 4096;
-  const char* names[5] = {"tf32 K-major SW128", "tf32 MN-major     ", "bf16 K-major SW128", "tf32 K-major SW32 ", "tf32 K-major SW64 "};
-  for (int mode = 0; mode < 5; ++mode)
-    for (int N : {64, 128, 192, 256}) {
-      for (int hammer : {0, 1}) {
+  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int niter = 4092;
+  const char* names[6] = {"tf32 K-major SW128", "tf32 MN-major     ", "bf16 K-major SW128", "tf32 K-major SW32 ", "tf32 K-major SW64 ", "tf32 3x pattern   "};
+  for (int mode : {0, 1, 5})
+    for (int N : {32, 64, 128, 192}) {
+      for (int hammer : {0}) {
         const int grid = 148;
-        probe<<<grid, 128, 100 * 1024>>>(N, mode, niter, hammer, d);
+        probe<<<grid, 128, 200 * 1024>>>(N, mode, niter, hammer, d);
         cudaError_t e = cudaDeviceSynchronize();
         long long cyc = 0;
         cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);

@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Development probe: per-CTA timeline inside conv_tc_kernel (needs the `make -C nvae_tf_b200/csrc dbg` build).
+usage (GPU box): NVAE_LIB=nvae_tf_b200/libnvae_b200_dbg.so python tools/tc_timeline.py N H W Cin Cout k [which]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from nvae_tf_b200 import runtime as R  # noqa: E402
+from nvae_tf_b200.layers import Conv2D  # noqa: E402
+
+
+def main():
+    N, H, W, Cin, Cout, k = [int(v) for v in sys.argv[1:7]]
+    which = int(sys.argv[7]) if len(sys.argv) > 7 else 0
+    rt = R.Runtime(seed=1)
+    with rt:
+        conv = Conv2D(Cout, (k, k), padding="same", in_channels=Cin, name="c")
+        rt.finalize()
+        rt.pack_plain(conv)
+        x = torch.randn(N, H, W, Cin, device="cuda")
+        y = torch.randn(N, H, W, Cout, device="cuda")
+        dx = torch.empty_like(x)
+        d = R.conv_desc(rt, tuple(x.shape), 0, conv.kernel.shape, 1)
+        ws, wsb = rt.workspace(256 << 20)
+        fn = [lambda: rt.lib.conv2d_fwd(C.byref(d), x.data_ptr(), None, conv.kernel.ptr(), conv.packed_fwd(), None, None,
+                                        y.data_ptr(), ws, wsb, rt.stream),
+              lambda: rt.lib.conv2d_dgrad(C.byref(d), y.data_ptr(), conv.kernel.ptr(), conv.packed_dgrad(), dx.data_ptr(),
+                                          None, 0, ws, wsb, rt.stream),
+              lambda: rt.lib.conv2d_wgrad(C.byref(d), x.data_ptr(), None, y.data_ptr(), conv.kernel.gptr(), None, ws, wsb,
+                                          rt.stream)][which]
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        buf = (C.c_ulonglong * (148 * 8))()
+        rc = rt.lib.dll.nvae_debug_tc_timing(buf)
+        t = np.array(buf, dtype=np.float64).reshape(148, 8)[:, :7]
+        t = t[t[:, 0] > 0]
+        t0 = t[:, 0].min()
+        t = (t - t0) / 1e3
+        names = ["start", "setup", "tile0", "mma_issued", "acc_done", "epi_done", "exit"]
+        print(f"rc={rc} event time {e0.elapsed_time(e1) * 1e3:.1f} us (incl. fix-up), {len(t)} CTAs; us since first CTA start:")
+        for i, n in enumerate(names):
+            print(f"  {n:11s} min {t[:, i].min():7.2f}  median {np.median(t[:, i]):7.2f}  max {t[:, i].max():7.2f}")
+
+
+if __name__ == "__main__":
+    main()
