@@ -104,6 +104,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand read from TMEM (lanes = rows, one 32-bit column per K element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrives on the mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -141,13 +161,13 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int n, int a_mn_major, int b
 #ifdef NVAE_TC_TIMING
 // development build only: per-CTA timestamps (ns, %globaltimer) [start, setup done, first tile landed, last MMA
 // issued, accumulator complete, epilogue done, exit]
-__device__ unsigned long long g_tc_timing[148 * 8];
+__device__ unsigned long long g_tc_timing[148 * 16];
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define TC_STAMP(i) g_tc_timing[blockIdx.x * 8 + (i)] = gtime()
+#define TC_STAMP(i) g_tc_timing[blockIdx.x * 16 + (i)] = gtime()
 extern "C" __attribute__((visibility("default"))) int nvae_debug_tc_timing(unsigned long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_tc_timing, sizeof(g_tc_timing));
 }
@@ -177,6 +197,15 @@ struct EpiSmem {
 __device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
   return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : 256u;
 }
+// TMEM columns. TF32: two accumulators of tmem_cols_for(BN).  3xTF32 (BN <= 192): all 512 columns -- accumulators
+// packed at [0, BN) and [BN, 2BN), and for forward/dgrad the A operand ring at 384: slot s = {hi 32 cols, lo 32 cols}.
+constexpr uint32_t kTmemAcol = 384;
+__device__ __forceinline__ uint32_t tmem_alloc_cols(int bn, int passes) {
+  return passes == 3 ? 512u : 2u * tmem_cols_for(bn);
+}
+__device__ __forceinline__ uint32_t tmem_acc_stride(int bn, int passes) {
+  return passes == 3 ? (uint32_t)bn : tmem_cols_for(bn);
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -191,6 +220,7 @@ struct TcParams {
   int N, H, W;
   int tw, th, tn, tiles_h;      // box extent; rows per box = tw*th*tn
   // tiles and the stream-K partition
+  int a_tmem;                   // 3xTF32: A (high and low parts) is staged in TMEM by the converters, only B lo in smem
   int BN, stages, lo_stages, passes;  // raw-tile ring, lo-tile ring (3xTF32 only); passes: 1 = TF32, 3 = 3xTF32
   int n_ntiles;                 // tile t = mt * n_ntiles + nt
   int KU;                       // k-units (pipeline stages) per tile
@@ -228,6 +258,29 @@ __device__ __forceinline__ int first_cta_of(const TcParams& p, int t, int G) {
   int c = (int)(x * G / p.U);
   while (cta_u0(p, c + 1, G) <= x) ++c;
   return c;
+}
+
+// Order in which a CTA walks its unit range [u_begin, u_end).  Natural order = ascending units.  For wgrad the K
+// axis is the pixel sweep: if the range opens with the tail of a tile (ka > 0) that piece is done LAST, so every
+// CTA starts at pixel 0 and all 148 sweep the activations in step -- the working set in L2 is a narrow pixel
+// window instead of both whole tensors (which thrash a 126 MB L2: 2 GB of DRAM reads for a 128 MB problem).
+struct SegOrder {
+  long long lo[2], hi[2];
+  int n;
+};
+__device__ __forceinline__ SegOrder seg_order(long long u_begin, long long u_end, int KU, bool pixel_sweep) {
+  SegOrder o;
+  const long long first_end = min(u_end, (u_begin / KU + 1) * (long long)KU);
+  if (pixel_sweep && u_begin % KU != 0 && first_end < u_end) {
+    o.n = 2;
+    o.lo[0] = first_end; o.hi[0] = u_end;
+    o.lo[1] = u_begin; o.hi[1] = first_end;
+  } else {
+    o.n = 1;
+    o.lo[0] = u_begin; o.hi[0] = u_end;
+    o.lo[1] = o.hi[1] = u_end;
+  }
+  return o;
 }
 
 // ---- epilogue addressing ----------------------------------------------------------------------------------
@@ -310,11 +363,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t stage_base = (smem_u32(smem_raw) + (uint32_t)sizeof(SmemCtl) + 1023u) & ~1023u;
   const uint32_t raw_bytes = p.a_bytes + p.b_bytes;
   const uint32_t stage_bytes = raw_bytes;                                   // raw ring: [A][B] per slot
-  const uint32_t lo_base = stage_base + (uint32_t)p.stages * raw_bytes;     // lo ring: [A lo][B lo] per slot
+  // lo ring.  a_tmem: [B lo] only -- A's high and low parts go to TMEM; else (wgrad with > 32 pixels per stage)
+  // [A lo][B lo] per slot
+  const uint32_t lo_base = stage_base + (uint32_t)p.stages * raw_bytes;
+  const uint32_t lo_bytes = p.a_tmem ? p.b_bytes : raw_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, cta = blockIdx.x;
   const long long u_begin = cta_u0(p, cta, G), u_end = cta_u0(p, cta + 1, G);
   const int nch = p.nchunk1 + p.nchunk2;
+  const SegOrder so = seg_order(u_begin, u_end, p.KU, WGRAD);
 
   if (threadIdx.x == 0) {
     TC_STAMP(0);
@@ -335,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     tma_prefetch_desc(&maps.m[0]);
     tma_prefetch_desc(&maps.m[2]);
   }
-  if (warp == 1) tmem_alloc(smem_u32(&ctl->tmem_base), 2u * tmem_cols_for(p.BN));
+  if (warp == 1) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_alloc_cols(p.BN, p.passes));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -346,7 +403,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       int it = 0;
-      for (long long u = u_begin; u < u_end;) {
+      for (int ph = 0; ph < so.n; ++ph)
+      for (long long u = so.lo[ph], u_end = so.hi[ph]; u < u_end;) {
         const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
         const int kb = (int)min((long long)p.KU, ka + (u_end - u));
         const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
@@ -414,14 +472,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       const uint32_t idesc = WGRAD ? umma_idesc_tf32(p.BN, 1, 1) : umma_idesc_tf32(p.BN, 0, 0);
+      const uint32_t idesc_ts = umma_idesc_tf32(p.BN, 0, WGRAD ? 1 : 0);  // A from TMEM is K-major by construction
       const uint32_t box_bytes = (uint32_t)p.KP * 128u;
       const int ksteps = WGRAD ? p.KP / 8 : 4;
       const uint64_t kadv = WGRAD ? 64u : 2u;  // descriptor start-address step per K=8: 8 pixel rows / 32 bytes
       int it = 0, seg = 0;
-      for (long long u = u_begin; u < u_end; ++seg) {
+      for (int ph = 0; ph < so.n; ++ph)
+      for (long long u = so.lo[ph], u_end = so.hi[ph]; u < u_end; ++seg) {
         const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
         const int kb = (int)min((long long)p.KU, ka + (u_end - u));
-        const uint32_t acc = tmem + (uint32_t)(seg & 1) * tmem_cols_for(p.BN);
+        const uint32_t acc = tmem + (uint32_t)(seg & 1) * tmem_acc_stride(p.BN, p.passes);
         mbar_wait(smem_u32(&ctl->acc_empty[seg & 1]), (((uint32_t)seg >> 1) & 1u) ^ 1u);
         tc_fence_after();
         for (int k = ka; k < kb; ++k, ++it) {
@@ -441,24 +501,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             da = umma_desc_sw128(sa, 16, 1024);
             db = umma_desc_sw128(sa + p.a_bytes, 16, 1024);
           }
-          // high parts first: they need nothing from the converters, which work on this stage meanwhile
-          for (int j = 0; j < ksteps; ++j)
-            umma_tf32(acc, da + kadv * j, db + kadv * j, idesc, (k > ka || j > 0) ? 1u : 0u);
+          if (!p.a_tmem) {
+            // high parts first: they need nothing from the converters, which work on this stage meanwhile
+            for (int j = 0; j < ksteps; ++j)
+              umma_tf32(acc, da + kadv * j, db + kadv * j, idesc, (k > ka || j > 0) ? 1u : 0u);
+          }
           if (p.passes == 3) {
             const int ls = it % p.lo_stages;
             mbar_wait(smem_u32(&ctl->conv[ls]), (uint32_t)(it / p.lo_stages) & 1u);
             tc_fence_after();
-            const uint32_t sl = lo_base + (uint32_t)ls * raw_bytes;
-            uint64_t la, lb;
-            if (WGRAD) {
-              la = umma_desc_sw128(sl, box_bytes, 512, 1);
-              lb = umma_desc_sw128(sl + p.a_bytes, box_bytes, 512, 1);
+            if (it == 8) TC_STAMP(14);
+            if (it == 9) TC_STAMP(15);
+            const uint32_t sl = lo_base + (uint32_t)ls * lo_bytes;
+            if (!p.a_tmem) {
+              const uint64_t la = umma_desc_sw128(sl, box_bytes, 512, 1);
+              const uint64_t lb = umma_desc_sw128(sl + p.a_bytes, box_bytes, 512, 1);
+              for (int j = 0; j < ksteps; ++j) umma_tf32(acc, da + kadv * j, lb + kadv * j, idesc, 1u);
+              for (int j = 0; j < ksteps; ++j) umma_tf32(acc, la + kadv * j, db + kadv * j, idesc, 1u);
             } else {
-              la = umma_desc_sw128(sl, 16, 1024);
-              lb = umma_desc_sw128(sl + p.a_bytes, 16, 1024);
+              // A (high and low parts) comes from TMEM: only B crosses the shared-memory port, three times
+              const uint64_t lb = WGRAD ? umma_desc_sw128(sl, box_bytes, 512, 1) : umma_desc_sw128(sl, 16, 1024);
+              const uint32_t a_hi = tmem + kTmemAcol + (uint32_t)ls * 64u, a_lo = a_hi + 32u;
+              for (int j = 0; j < 4; ++j)
+                umma_tf32_ts(acc, a_hi + 8u * j, db + kadv * j, idesc_ts, (k > ka || j > 0) ? 1u : 0u);
+              for (int j = 0; j < 4; ++j) umma_tf32_ts(acc, a_hi + 8u * j, lb + kadv * j, idesc_ts, 1u);
+              for (int j = 0; j < 4; ++j) umma_tf32_ts(acc, a_lo + 8u * j, db + kadv * j, idesc_ts, 1u);
             }
-            for (int j = 0; j < ksteps; ++j) umma_tf32(acc, da + kadv * j, lb + kadv * j, idesc, 1u);
-            for (int j = 0; j < ksteps; ++j) umma_tf32(acc, la + kadv * j, db + kadv * j, idesc, 1u);
             umma_commit(smem_u32(&ctl->lo_empty[ls]));
           }
           umma_commit(smem_u32(&ctl->empty[st]));
@@ -478,13 +546,57 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int st = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         const int ls = it % p.lo_stages;
+        if (it == 8 && ct == 0) TC_STAMP(8);
         mbar_wait(smem_u32(&ctl->lo_empty[ls]), ((uint32_t)(it / p.lo_stages) & 1u) ^ 1u);
+        if (it == 8 && ct == 0) TC_STAMP(9);
         mbar_wait(smem_u32(&ctl->full[st]), ph);
-        const float4* src = reinterpret_cast<const float4*>(smem_raw + (stage_base - smem_u32(smem_raw)) +
-                                                            (size_t)st * stage_bytes);
-        float4* dst = reinterpret_cast<float4*>(smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)ls * raw_bytes);
+        if (it == 8 && ct == 0) TC_STAMP(10);
+        const uint8_t* raw = smem_raw + (stage_base - smem_u32(smem_raw)) + (size_t)st * stage_bytes;
+        uint8_t* lo = smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)ls * lo_bytes;
+        const float4* src;
+        float4* dst;
+        int n16c;
+        if (!p.a_tmem) {
+          src = reinterpret_cast<const float4*>(raw);
+          dst = reinterpret_cast<float4*>(lo);
+          n16c = n16;
+        } else {
+          const int half = (warp - 2) >> 2;  // two warps share a TMEM lane group: K columns [16*half, +16)
+          uint32_t hi[16], lw[16];
+          if (!WGRAD) {
+            // A: tile row m (128 B, 8 swizzled 16-byte chunks) -> TMEM lane m
+            const int m = (warp & 3) * 32 + lane;
+            const float4* arow = reinterpret_cast<const float4*>(raw + m * 128);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 v = arow[(half * 4 + c) ^ (m & 7)];
+              const float4 l = tf32_lo4(v);
+              hi[4 * c] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+              hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+              lw[4 * c] = __float_as_uint(l.x); lw[4 * c + 1] = __float_as_uint(l.y);
+              lw[4 * c + 2] = __float_as_uint(l.z); lw[4 * c + 3] = __float_as_uint(l.w);
+            }
+          } else {
+            // A^T: lane m = (job, channel); K = the 32 pixels of the box.  Box layout: pixel rows of 128 B whose
+            // 32-byte units are XOR-swizzled with (row & 3) (128B swizzle, 32-byte atoms)
+            const float* box = reinterpret_cast<const float*>(raw + (size_t)(warp & 3) * p.KP * 128);
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+              const int k = half * 16 + kk;
+              const float v = box[k * 32 + ((((lane >> 3) ^ (k & 3)) << 3) | (lane & 7))];
+              hi[kk] = __float_as_uint(v);
+              lw[kk] = __float_as_uint(tf32_lo(v));
+            }
+          }
+          const uint32_t ta = tmem + kTmemAcol + (uint32_t)ls * 64u + (uint32_t)half * 16u + ((uint32_t)((warp & 3) * 32) << 16);
+          tmem_st16(ta, hi);
+          tmem_st16(ta + 32u, lw);
+          src = reinterpret_cast<const float4*>(raw + p.a_bytes);
+          dst = reinterpret_cast<float4*>(lo);
+          n16c = (int)(p.b_bytes >> 4);
+        }
         int i = ct;
-        for (; i + 3 * kConvThreads < n16; i += 4 * kConvThreads) {  // loads first: 4 independent LDS.128 in flight
+        for (; i + 3 * kConvThreads < n16c; i += 4 * kConvThreads) {  // loads first: 4 independent LDS.128 in flight
           const float4 v0 = src[i], v1 = src[i + kConvThreads], v2 = src[i + 2 * kConvThreads],
                        v3 = src[i + 3 * kConvThreads];
           dst[i] = tf32_lo4(v0);
@@ -492,20 +604,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           dst[i + 2 * kConvThreads] = tf32_lo4(v2);
           dst[i + 3 * kConvThreads] = tf32_lo4(v3);
         }
-        for (; i < n16; i += kConvThreads) dst[i] = tf32_lo4(src[i]);
+        for (; i < n16c; i += kConvThreads) dst[i] = tf32_lo4(src[i]);
+        if (it == 8 && ct == 0) TC_STAMP(11);
+        if (p.a_tmem) {
+          tmem_st_wait();
+          tc_fence_before();
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&ctl->conv[ls]));
+        if (it == 8 && ct == 0) TC_STAMP(12);
+        if (it == 9 && ct == 0) TC_STAMP(13);
       }
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> smem transpose -> global (final tile or raw partial) ----
     const int lg = warp & 3;  // TMEM lane group this warp may read: lanes [32*lg, +32)
     const int row = lg * 32 + lane;
-    EpiSmem* epi = reinterpret_cast<EpiSmem*>(smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)p.lo_stages * raw_bytes);
+    EpiSmem* epi = reinterpret_cast<EpiSmem*>(smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)p.lo_stages * lo_bytes);
     const int q = lane & 7, r0 = lane >> 3;
     int seg = 0;
-    for (long long u = u_begin; u < u_end; ++seg) {
+    for (int ph = 0; ph < so.n; ++ph)
+    for (long long u = so.lo[ph], u_end = so.hi[ph]; u < u_end; ++seg) {
       const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
       const int kb = (int)min((long long)p.KU, ka + (u_end - u));
       const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
@@ -516,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       // slot 0: continues a tile begun by an earlier CTA; slot 1: begins a tile a later CTA finishes
       float* pdst = p.part + (((int64_t)cta * 2 + (ka > 0 ? 0 : 1)) * kBM + lg * 32) * p.BN;
-      const uint32_t acc = tmem + (uint32_t)(seg & 1) * tmem_cols_for(p.BN) + ((uint32_t)(lg * 32) << 16);
+      const uint32_t acc = tmem + (uint32_t)(seg & 1) * tmem_acc_stride(p.BN, p.passes) + ((uint32_t)(lg * 32) << 16);
       mbar_wait(smem_u32(&ctl->acc_full[seg & 1]), ((uint32_t)seg >> 1) & 1u);
       tc_fence_after();
       if (threadIdx.x == kThreads - 1) TC_STAMP(4);
@@ -555,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 2u * tmem_cols_for(p.BN));
+    tmem_dealloc(tmem, tmem_alloc_cols(p.BN, p.passes));
     if (lane == 0) TC_STAMP(6);
   }
 }
@@ -700,7 +820,7 @@ bool common_ok(const NvaeConvDesc* d) {
 // Launch plan shared by the three directions: tiles, stages, stream-K grid, partial-buffer size.
 struct Plan {
   PixTile t;
-  int BN, stages, lo_stages, n_mtiles, n_ntiles, KU, G, njobs;
+  int BN, stages, lo_stages, a_tmem, n_mtiles, n_ntiles, KU, G, njobs;
   uint32_t a_bytes, b_bytes;
   long long U;
   int whole_tiles;
@@ -713,20 +833,24 @@ struct Plan {
 // fix-up launch, so it is done only when the main loop it shortens is longer than that (small spatial scales:
 // 18-72 tiles, K up to 2304).  Times in microseconds, calibrated on B200 (one 32-deep K stage ~ 0.95 us in
 // 3xTF32, 0.35 us in TF32; fix-up ~ 5 us + partial traffic at ~3 TB/s).
-bool finish_plan(Plan* pl, int passes) {
+bool finish_plan(Plan* pl, int passes, bool wgrad) {
   const size_t raw = (size_t)pl->a_bytes + pl->b_bytes;
-  int slots = (int)((kSmemBudget - 2048) / raw);
-  if (passes == 3) {  // raw ring + lo ring: the TMA latency needs the depth, the converters only a double buffer
-    if (slots < 3) return false;
-    pl->lo_stages = slots >= 5 ? 2 : 1;
-    pl->stages = slots - pl->lo_stages;
+  const size_t budget = (size_t)kSmemBudget - 2048;
+  size_t lo_slot = 0;
+  if (passes == 3) {  // raw ring for the TMA latency + a double-buffered lo ring (wgrad: A and B; fwd/dgrad: B only)
+    pl->a_tmem = (!wgrad || pl->a_bytes == 4u * 32u * 128u) ? 1 : 0;  // wgrad: 32 pixels per stage fit the TMEM A ring
+    lo_slot = pl->a_tmem ? pl->b_bytes : raw;
+    pl->lo_stages = 2;
+    if (budget < 2 * lo_slot + 2 * raw) return false;
+    pl->stages = (int)((budget - 2 * lo_slot) / raw);
   } else {
-    if (slots < 2) return false;
+    if (budget < 2 * raw) return false;
     pl->lo_stages = 0;
-    pl->stages = slots;
+    pl->a_tmem = 0;
+    pl->stages = (int)(budget / raw);
   }
   if (pl->stages > kMaxStages) pl->stages = kMaxStages;
-  pl->smem = sizeof(SmemCtl) + 1024 + (size_t)(pl->stages + pl->lo_stages) * raw + sizeof(EpiSmem);
+  pl->smem = sizeof(SmemCtl) + 1024 + (size_t)pl->stages * raw + (size_t)pl->lo_stages * lo_slot + sizeof(EpiSmem);
   const long long T = (long long)pl->n_mtiles * pl->n_ntiles;
   pl->U = T * pl->KU;
   const double t_unit = passes == 3 ? 0.95 : 0.35;
@@ -734,14 +858,15 @@ bool finish_plan(Plan* pl, int passes) {
   pl->whole_tiles = 1;
   pl->G = (int)(T < kNumSMs ? T : kNumSMs);
   double best = (double)ceil_div(T, pl->G) * pl->KU * t_unit;
-  if (T >= kNumSMs) {
-    const double sk = (double)pl->U / kNumSMs * t_unit + 5.0 + 2.0 * kNumSMs * slot_us;
-    if (sk < best) { pl->whole_tiles = 0; pl->G = kNumSMs; }
-  } else {
+  if (T < kNumSMs) {
     for (int S = 2; S * T <= kNumSMs && 2 * S <= pl->KU; ++S) {  // S CTAs per tile, >= 2 stages each
       const double t = (double)ceil_div(pl->KU, S) * t_unit + 5.0 + (double)S * T * slot_us;
       if (t < best) { best = t; pl->whole_tiles = 0; pl->G = (int)(S * T); }
     }
+  }
+  if (pl->U >= 2 * kNumSMs) {  // equal unit ranges over all SMs (up to two partials per CTA)
+    const double sk = (double)ceil_div(pl->U, kNumSMs) * t_unit + 5.0 + 2.0 * kNumSMs * slot_us;
+    if (sk < 0.95 * best) { best = sk; pl->whole_tiles = 0; pl->G = kNumSMs; }
   }
   pl->split = !pl->whole_tiles;
   pl->part_bytes = pl->split ? al256((size_t)pl->G * 2 * kBM * pl->BN * sizeof(float)) : 0;
@@ -762,7 +887,7 @@ bool plan_gemm(const NvaeConvDesc* d, int which, Plan* pl) {
   pl->a_bytes = kBM * 128;
   pl->b_bytes = (uint32_t)pl->BN * 128;
   pl->njobs = 0;
-  return finish_plan(pl, passes);
+  return finish_plan(pl, passes, false);
 }
 
 bool plan_wgrad(const NvaeConvDesc* d, Plan* pl) {
@@ -776,20 +901,20 @@ bool plan_wgrad(const NvaeConvDesc* d, Plan* pl) {
   pl->njobs = d->R * d->S * nch;
   pl->n_mtiles = (pl->njobs + 3) / 4;
   pl->BN = pick_bn(d->Cout, 32, passes == 3 ? 192 : 256);
-  // at least 3 raw + 2 lo (3xTF32) / 3 raw (TF32) slots in shared memory
-  const size_t want = passes == 3 ? 5 : 3;
+  // at least 2 raw + 2 lo (3xTF32) / 3 raw (TF32) slots in shared memory
+  const size_t want = passes == 3 ? 4 : 3;
   while ((size_t)(4 + pl->BN / kChunk) * KP * 128 * want > (size_t)kSmemBudget - 2048 && pl->BN > 32) pl->BN -= 32;
   pl->n_ntiles = (int)ceil_div(d->Cout, pl->BN);
   pl->KU = pl->t.n_tiles;
   pl->a_bytes = 4u * KP * 128u;
   pl->b_bytes = (uint32_t)(pl->BN / kChunk) * KP * 128u;
-  return finish_plan(pl, passes);
+  return finish_plan(pl, passes, true);
 }
 
 void fill_common(TcParams* p, const NvaeConvDesc* d, const Plan& pl, float* part) {
   p->N = d->N; p->H = d->H; p->W = d->W;
   p->tw = pl.t.tw; p->th = pl.t.th; p->tn = pl.t.tn; p->tiles_h = pl.t.tiles_h;
-  p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
+  p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
   p->n_ntiles = pl.n_ntiles; p->KU = pl.KU; p->U = pl.U;
   p->T = pl.n_mtiles * pl.n_ntiles; p->whole_tiles = pl.whole_tiles;
   p->a_bytes = pl.a_bytes; p->b_bytes = pl.b_bytes;

@@ -38,7 +38,12 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int mode, int niter, int 
   __shared__ uint32_t tmem_base;
   __shared__ volatile int done;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  for (int i = threadIdx.x; i < 196 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0;
+  for (int i = threadIdx.x; i < 196 * 1024 / 4; i += blockDim.x) {
+    // hammer==2: random finite floats in [1,2) (realistic toggling / power); else zeros
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    reinterpret_cast<uint32_t*>(smem_raw)[i] = hammer == 2 ? (0x3F800000u | (h & 0x007FFFFFu)) : 0u;
+  }
   if (threadIdx.x == 0) {
     done = 0;
     mbar_init(smem_u32(&bar), 1);
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int mode, int niter, int 
     t1 = clock64();
     done = 1;
     if (blockIdx.x == 0) out[0] = t1 - t0;
-  } else if (hammer && threadIdx.x >= 32) {
+  } else if (hammer == 1 && threadIdx.x >= 32) {
     float4* reg = reinterpret_cast<float4*>(smem_raw + 1024 + 16384 + 32768);  // 32 KB scratch after A and B
     const int t = threadIdx.x - 32;
     float4 acc = make_float4(0, 0, 0, 0);
@@ -129,11 +134,11 @@ int main() {
   long long* d;
   cudaMalloc(&d, 16);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const int niter = 4092;
+  const int niter = 4092 * 16;
   const char* names[6] = {"tf32 K-major SW128", "tf32 MN-major     ", "bf16 K-major SW128", "tf32 K-major SW32 ", "tf32 K-major SW64 ", "tf32 3x pattern   "};
   for (int mode : {0, 1, 5})
     for (int N : {32, 64, 128, 192}) {
-      for (int hammer : {0}) {
+      for (int hammer : {0, 2}) {
         const int grid = 148;
         probe<<<grid, 128, 200 * 1024>>>(N, mode, niter, hammer, d);
         cudaError_t e = cudaDeviceSynchronize();

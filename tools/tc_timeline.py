@@ -41,13 +41,17 @@ def main():
         fn()
         e1.record()
         torch.cuda.synchronize()
-        buf = (C.c_ulonglong * (148 * 8))()
+        print(f"event time {e0.elapsed_time(e1) * 1e3:.1f} us (incl. fix-up)")
+        if not hasattr(rt.lib.dll, "nvae_debug_tc_timing"):
+            return  # regular build: timing only (this script doubles as the single-kernel workload for ncu)
+        buf = (C.c_ulonglong * (148 * 16))()
         rc = rt.lib.dll.nvae_debug_tc_timing(buf)
-        t = np.array(buf, dtype=np.float64).reshape(148, 8)[:, :7]
+        t = np.array(buf, dtype=np.float64).reshape(148, 16)
         t = t[t[:, 0] > 0]
         t0 = t[:, 0].min()
         t = (t - t0) / 1e3
-        names = ["start", "setup", "tile0", "mma_issued", "acc_done", "epi_done", "exit"]
+        names = ["start", "setup", "tile0", "mma_issued", "acc_done", "epi_done", "exit", "-", "cv8 begin", "cv8 lo_empty", "cv8 full",
+                 "cv8 converted", "cv8 arrived", "cv9 arrived", "mma8 conv ok", "mma9 conv ok"]
         print(f"rc={rc} event time {e0.elapsed_time(e1) * 1e3:.1f} us (incl. fix-up), {len(t)} CTAs; us since first CTA start:")
         for i, n in enumerate(names):
             print(f"  {n:11s} min {t[:, i].min():7.2f}  median {np.median(t[:, i]):7.2f}  max {t[:, i].max():7.2f}")
