@@ -102,49 +102,35 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float* __res
   }
 }
 
-// Combines the per-CTA (mean, M2) partials: block = 32 channels x 8 split lanes, two passes of plain sums
-// (mean = sum n_s*m_s / n;  M2 = sum q_s + n_s*(m_s - mean)^2) so no serial chain of divisions; fixed order.
+// Combines the per-CTA (mean, M2) partials: one warp per channel, lane l takes splits l, l+32, ...; two passes of
+// plain sums (mean = sum n_s*m_s / n;  M2 = sum q_s + n_s*(m_s - mean)^2) and a fixed shuffle tree -- no serial
+// chain of divisions, deterministic.
 __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t rows,
                                                           int64_t rows_per_split, int C,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* __restrict__ mm,
                                                           float* __restrict__ mv, int training, float momentum,
                                                           float eps, float* __restrict__ stat) {
-  __shared__ double sm[8][33];
-  const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
-  const bool ok = c < C;
-  float mean = 0.f, var = 1.f;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;
+  float mean, var;
   if (training) {
     const double n = (double)rows;
+    const double n_last = (double)(rows - (int64_t)(nsplit - 1) * rows_per_split), n_full = (double)rows_per_split;
     double acc = 0;
-    if (ok)
-      for (int s = sy; s < nsplit; s += 8) {
-        const int64_t r0 = (int64_t)s * rows_per_split;
-        const double nb = (double)((r0 + rows_per_split < rows ? r0 + rows_per_split : rows) - r0);
-        acc += nb * part[((int64_t)s * 2) * C + c];
-      }
-    sm[sy][cx] = acc;
-    __syncthreads();
-    double mu = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) mu += sm[k][cx];
-    mu /= n;
-    __syncthreads();
+#pragma unroll 4
+    for (int s = lane; s < nsplit; s += 32)
+      acc += (s == nsplit - 1 ? n_last : n_full) * part[((int64_t)s * 2) * C + c];
+    const double mu = warp_sum(acc) / n;
     acc = 0;
-    if (ok)
-      for (int s = sy; s < nsplit; s += 8) {
-        const int64_t r0 = (int64_t)s * rows_per_split;
-        const double nb = (double)((r0 + rows_per_split < rows ? r0 + rows_per_split : rows) - r0);
-        const double d = part[((int64_t)s * 2) * C + c] - mu;
-        acc += part[((int64_t)s * 2 + 1) * C + c] + nb * d * d;
-      }
-    sm[sy][cx] = acc;
-    __syncthreads();
-    if (sy != 0 || !ok) return;
-    double M2 = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) M2 += sm[k][cx];
+#pragma unroll 4
+    for (int s = lane; s < nsplit; s += 32) {
+      const double d = part[((int64_t)s * 2) * C + c] - mu;
+      acc += part[((int64_t)s * 2 + 1) * C + c] + (s == nsplit - 1 ? n_last : n_full) * d * d;
+    }
+    const double M2 = warp_sum(acc);
+    if (lane != 0) return;
     mean = (float)mu;
     var = (float)(M2 / n);
     if (mm != nullptr) {
@@ -153,7 +139,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restri
       mv[c] = mv[c] * momentum + (float)unbiased * (1.f - momentum);
     }
   } else {
-    if (sy != 0 || !ok) return;
+    if (lane != 0) return;
     mean = mm[c];
     var = mv[c];
   }
@@ -262,22 +248,18 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const float* 
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const double* __restrict__ part, int nsplit,
                                                               int64_t rows, int C, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, float* __restrict__ bstat) {
-  __shared__ double sm[2][8][33];
-  const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);  // one warp per channel
+  if (c >= C) return;
   double sg = 0, sq = 0;
-  if (c < C)
-    for (int s = sy; s < nsplit; s += 8) {
-      sg += part[((int64_t)s * 2) * C + c];
-      sq += part[((int64_t)s * 2 + 1) * C + c];
-    }
-  sm[0][sy][cx] = sg;
-  sm[1][sy][cx] = sq;
-  __syncthreads();
-  if (sy != 0 || c >= C) return;
-  sg = sq = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { sg += sm[0][k][cx]; sq += sm[1][k][cx]; }
+#pragma unroll 4
+  for (int s = lane; s < nsplit; s += 32) {
+    sg += part[((int64_t)s * 2) * C + c];
+    sq += part[((int64_t)s * 2 + 1) * C + c];
+  }
+  sg = warp_sum(sg);
+  sq = warp_sum(sq);
+  if (lane != 0) return;
   if (dgamma) dgamma[c] = (float)sq;
   if (dbeta) dbeta[c] = (float)sg;
   bstat[c] = (float)(sg / (double)rows);
@@ -354,7 +336,7 @@ extern "C" int nvae_bn_stats(const float* x, int64_t rows, int C, const float* g
     bn_stats_kernel<<<dim3(g.nchunk, g.nsplit), kBnThreads, 0, stream>>>(x, rows, C, g.rows_per_split, g.LC, part);
     NVAE_RETURN_IF_LAUNCH_FAILED();
   }
-  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, stream>>>(part, g.nsplit, rows, g.rows_per_split, C, gamma, beta,
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(part, g.nsplit, rows, g.rows_per_split, C, gamma, beta,
                                                            moving_mean, moving_var, training, momentum, eps, stat);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
@@ -399,7 +381,7 @@ static int bn_act_bwd_impl(const float* dout, const float* x, int64_t rows, int 
     bn_bwd_reduce_kernel<ACT><<<dim3(g.nchunk, g.nsplit), kBnThreads, 0, stream>>>(dout, x, rows, C, g.rows_per_split,
                                                                                   g.LC, stat, up_h, up_w, part);
     NVAE_RETURN_IF_LAUNCH_FAILED();
-    bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, stream>>>(part, g.nsplit, rows, C, dgamma, dbeta, bs);
+    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(part, g.nsplit, rows, C, dgamma, dbeta, bs);
     NVAE_RETURN_IF_LAUNCH_FAILED();
     if (training) bstat = bs;
   }

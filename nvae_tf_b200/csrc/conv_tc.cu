@@ -681,10 +681,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 }
 
 // Fix-up: block (c, y) finishes the tile whose K range ENDS inside CTA c's first segment: sums the partials of
-// the CTAs that covered it, in CTA order, and applies the epilogue.  kFixRows tile rows per blockIdx.y.
-constexpr int kFixRows = 4;
+// the CTAs that covered it and applies the epilogue.  `rows` tile rows per blockIdx.y.  The partial list of a
+// tile (up to 148 deep when one tile is all there is) is cut over KG thread groups -- group g sums partials
+// g, g+KG, ... in order, four loads in flight -- and the group sums are combined in group order: a fixed tree,
+// so results are bit-repeatable.
+constexpr int kFixThreads = 256;
+constexpr int kFixMaxGroups = 8;
 template <bool WGRAD>
-__global__ void __launch_bounds__(256) conv_tc_fixup_kernel(const TcParams p, int G) {
+__global__ void __launch_bounds__(kFixThreads) conv_tc_fixup_kernel(const TcParams p, int G, int rows) {
+  __shared__ float4 red[kFixThreads];
   const int c = blockIdx.x;
   const long long u0 = cta_u0(p, c, G), u1 = cta_u0(p, c + 1, G);
   const int t = (int)(u0 / p.KU);
@@ -692,26 +697,69 @@ __global__ void __launch_bounds__(256) conv_tc_fixup_kernel(const TcParams p, in
   if (u1 < (long long)(t + 1) * p.KU) return;          // ... or does not finish the tile
   const int cf = first_cta_of(p, t, G);
   const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
-  const int bn4 = p.BN / 4;
+  const int bn4 = p.BN / 4, total = rows * bn4, nparts = c - cf + 1;
   const int64_t slot = (int64_t)kBM * p.BN;
-  for (int i = threadIdx.x; i < kFixRows * bn4; i += blockDim.x) {
-    const int row = blockIdx.y * kFixRows + i / bn4, col = (i % bn4) * 4;
-    const int64_t o = (int64_t)row * p.BN + col;
-    float4 s = ldg4(p.part + ((int64_t)cf * 2 + 1) * slot + o);
-    int k = cf + 1;
-    for (; k + 3 <= c; k += 4) {  // four independent loads in flight; the additions keep CTA order
-      const float4 v0 = ldg4(p.part + ((int64_t)k * 2) * slot + o), v1 = ldg4(p.part + ((int64_t)(k + 1) * 2) * slot + o),
-                   v2 = ldg4(p.part + ((int64_t)(k + 2) * 2) * slot + o),
-                   v3 = ldg4(p.part + ((int64_t)(k + 3) * 2) * slot + o);
+  const int64_t blk = (int64_t)blockIdx.y * rows * p.BN;
+  // partial j of the tile: j = 0 -> CTA cf's slot 1 (it began the tile), j >= 1 -> CTA cf+j's slot 0
+  auto part_ptr = [&](int j) { return p.part + ((int64_t)(cf + j) * 2 + (j == 0 ? 1 : 0)) * slot + blk; };
+  int KG = kFixThreads / total;
+  KG = KG < 1 ? 1 : (KG > kFixMaxGroups ? kFixMaxGroups : KG);
+  if (KG > nparts) KG = nparts;
+  if (KG == 1) {
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * kFixThreads) {
+      float4 s[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * kFixThreads;
+        s[j] = i < total ? ldg4(part_ptr(0) + (int64_t)i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int k = 1; k < nparts; ++k) {
+        const float* pk = part_ptr(k);
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j * kFixThreads;
+          v[j] = i < total ? ldg4(pk + (int64_t)i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s[j].x += v[j].x; s[j].y += v[j].y; s[j].z += v[j].z; s[j].w += v[j].w; }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * kFixThreads;
+        if (i < total) {
+          const int row = blockIdx.y * rows + i / bn4, col = (i % bn4) * 4;
+          store4<WGRAD>(p, row_ctx<WGRAD>(p, mt, row), nt, col, s[j]);
+        }
+      }
+    }
+    return;
+  }
+  const int g = threadIdx.x / total, e = threadIdx.x - g * total;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g < KG) {
+    int k = g;
+    for (; k + 3 * KG < nparts; k += 4 * KG) {
+      const float4 v0 = ldg4(part_ptr(k) + (int64_t)e * 4), v1 = ldg4(part_ptr(k + KG) + (int64_t)e * 4),
+                   v2 = ldg4(part_ptr(k + 2 * KG) + (int64_t)e * 4), v3 = ldg4(part_ptr(k + 3 * KG) + (int64_t)e * 4);
       s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
       s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
       s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
       s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
     }
-    for (; k <= c; ++k) {
-      const float4 v = ldg4(p.part + ((int64_t)k * 2) * slot + o);
+    for (; k < nparts; k += KG) {
+      const float4 v = ldg4(part_ptr(k) + (int64_t)e * 4);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
+    red[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (g == 0) {
+    for (int q = 1; q < KG; ++q) {
+      const float4 v = red[q * total + e];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const int row = blockIdx.y * rows + e / bn4, col = (e % bn4) * 4;
     store4<WGRAD>(p, row_ctx<WGRAD>(p, mt, row), nt, col, s);
   }
 }
@@ -932,7 +980,12 @@ int launch(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t 
   conv_tc_kernel<WGRAD><<<pl.G, kThreads, pl.smem, stream>>>(maps, p);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   if (pl.split) {
-    conv_tc_fixup_kernel<WGRAD><<<dim3(pl.G, kBM / kFixRows), 256, 0, stream>>>(p, pl.G);
+    // few split tiles -> fewer rows per block, so the fix-up still fills the machine and sums partials in parallel
+    const long long T = (long long)pl.n_mtiles * pl.n_ntiles;
+    const long long tiles = T < pl.G ? T : pl.G;
+    int rows = 32;
+    while (rows > 1 && tiles * (kBM / rows) < 2 * kNumSMs) rows >>= 1;
+    conv_tc_fixup_kernel<WGRAD><<<dim3(pl.G, kBM / rows), kFixThreads, 0, stream>>>(p, pl.G, rows);
     NVAE_RETURN_IF_LAUNCH_FAILED();
   }
   return NVAE_OK;

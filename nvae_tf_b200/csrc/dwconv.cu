@@ -33,6 +33,8 @@ static DwGeom dw_geom(int N, int H, int W, int C) {
 }
 
 // Stage `imgs` images of the channel chunk into the haloed tile, applying act(x*scale+shift).
+// Two passes so no thread ever waits on one load at a time: the tile is zero-filled (stores only), then the
+// valid pixels are copied with four independent 128-bit loads in flight per thread.
 template <bool PROLOGUE>
 __device__ __forceinline__ void dw_stage(float* tile, const float* __restrict__ x, const float* __restrict__ stat,
                                          int act, int n0, int nimg, int H, int W, int C, int c0, int PH, int PW) {
@@ -42,19 +44,31 @@ __device__ __forceinline__ void dw_stage(float* tile, const float* __restrict__ 
     sc = ldg4(stat + 2 * C + c0 + c4 * 4);
     sh = ldg4(stat + 3 * C + c0 + c4 * 4);
   }
-  const int total = nimg * PH * PW;
-  for (int p = threadIdx.x >> 3; p < total; p += kDwThreads >> 3) {
-    const int pw = p % PW, t = p / PW, ph = t % PH, im = t / PH;
-    const int h = ph - 2, w = pw - 2;
-    float4 v = make_float4(0, 0, 0, 0);
-    if (h >= 0 && h < H && w >= 0 && w < W) {
-      v = ldg4(x + (((int64_t)(n0 + im) * H + h) * W + w) * C + c0 + c4 * 4);
-      if (PROLOGUE) {
-        v.x = act_fwd_rt(fmaf(v.x, sc.x, sh.x), act); v.y = act_fwd_rt(fmaf(v.y, sc.y, sh.y), act);
-        v.z = act_fwd_rt(fmaf(v.z, sc.z, sh.z), act); v.w = act_fwd_rt(fmaf(v.w, sc.w, sh.w), act);
-      }
+  const int total4 = nimg * PH * PW * (kDwCC / 4);
+  for (int i = threadIdx.x; i < total4; i += kDwThreads)
+    reinterpret_cast<float4*>(tile)[i] = make_float4(0, 0, 0, 0);
+  __syncthreads();
+  const int HW = H * W, npix = nimg * HW;
+  constexpr int kStep = kDwThreads >> 3, kBatch = 4;
+  const float* xb = x + (int64_t)n0 * HW * C + c0 + c4 * 4;
+  for (int p0 = threadIdx.x >> 3; p0 < npix; p0 += kStep * kBatch) {
+    float4 v[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int p = p0 + j * kStep;
+      v[j] = p < npix ? ldg4(xb + (int64_t)p * C) : make_float4(0, 0, 0, 0);
     }
-    *reinterpret_cast<float4*>(tile + (size_t)p * kDwCC + c4 * 4) = v;
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int p = p0 + j * kStep;
+      if (p >= npix) continue;
+      if (PROLOGUE) {
+        v[j].x = act_fwd_rt(fmaf(v[j].x, sc.x, sh.x), act); v[j].y = act_fwd_rt(fmaf(v[j].y, sc.y, sh.y), act);
+        v[j].z = act_fwd_rt(fmaf(v[j].z, sc.z, sh.z), act); v[j].w = act_fwd_rt(fmaf(v[j].w, sc.w, sh.w), act);
+      }
+      const int im = p / HW, q = p - im * HW, h = q / W, w = q - h * W;
+      *reinterpret_cast<float4*>(tile + ((size_t)(im * PH + h + 2) * PW + w + 2) * kDwCC + c4 * 4) = v[j];
+    }
   }
 }
 
@@ -122,9 +136,23 @@ __global__ void __launch_bounds__(kDwThreads) dwconv5x5_bwd_filter_kernel(
   dw_stage<true>(tile, x, stat, act, n0, nimg, H, W, C, c0, PH, PW);
   const int c4 = threadIdx.x & 7;
   const int npix = nimg * H * W;
-  for (int p = threadIdx.x >> 3; p < npix; p += kDwThreads >> 3)
-    *reinterpret_cast<float4*>(dtile + (size_t)p * kDwCC + c4 * 4) =
-        ldg4(dy + ((int64_t)n0 * H * W + p) * C + c0 + c4 * 4);
+  {
+    constexpr int kStep = kDwThreads >> 3, kBatch = 4;
+    const float* db = dy + (int64_t)n0 * H * W * C + c0 + c4 * 4;
+    for (int p0 = threadIdx.x >> 3; p0 < npix; p0 += kStep * kBatch) {
+      float4 v[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int p = p0 + j * kStep;
+        v[j] = p < npix ? ldg4(db + (int64_t)p * C) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int p = p0 + j * kStep;
+        if (p < npix) *reinterpret_cast<float4*>(dtile + (size_t)p * kDwCC + c4 * 4) = v[j];
+      }
+    }
+  }
   __syncthreads();
   const int tap = threadIdx.x >> 3;  // 0..31; 25 = bias, >25 idle
   if (tap > 25) return;
