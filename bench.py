@@ -276,16 +276,24 @@ def main():
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel, live ----------------------------------------------------------------
     dom = measure_dominant_kernel(model)["conv_fwd"]
     tc = precision != _lib.NVAE_PREC_FP32
+    x3 = precision == _lib.NVAE_PREC_TF32X3
     bf16_peak = peaks.get("bf16_tflops", 1590.0)
     peak = bf16_peak / 2.0  # TF32 = half the bf16 rate (nominal ratio) of the measured/fallback bf16 burst figure
     achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
-                "kernel": ("conv_tc_fwd (tcgen05 kind::tf32 implicit GEMM)" if tc else
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01d_*.md);
+                # algorithmic bytes are 127.9 MB (x + w + y once)
+                "traffic": 127.0e6 if x3 else None,
+                "mma_issue_factor": 3 if x3 else 1,
+                "note": ("3xTF32 issues 3 MMAs per algorithmic product, so its ceiling is peak/3; "
+                         "frac is algorithmic FLOP/s over the full TF32 peak") if x3 else "",
+                "kernel": ("conv_tc_kernel<false> (tcgen05 kind::tf32 implicit GEMM, TMA-staged, "
+                           + ("3xTF32 split in-kernel, A via TMEM" if x3 else "single-pass TF32") + ")" if tc else
                            "simt_conv_kernel<FwdProb> (fp32 CUDA-core implicit GEMM)"),
                 "shape": "postprocess cbs2 5x5 384->384 @16x16, batch 144: M=36864 N=384 K=9600",
                 "flops_per_launch": dom["flops"], "ms_per_launch": dom["ms"],
@@ -296,7 +304,7 @@ def main():
     cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(args.cpu_batch)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32" if tc else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": ("tf32x3" if x3 else "tf32") if tc else "f32", "data": "synthetic",
             "config": {"workload": "full MNIST-config NVAE train step (train.py defaults: 40.1M params, 15 latent "
                                    "groups, KL+recon+BN-gamma loss, SN, Adamax), BASELINE configs[2]",
                        "batch_per_gpu": B, "global_batch": B * world, "image": "32x32x1",
@@ -308,6 +316,7 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -75,6 +75,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -231,7 +238,12 @@ struct TcParams {
   float* part;                  // [gridDim.x][2][128][BN] raw partial accumulators
   // forward / dgrad: K loop and epilogue
   int taps, S;
-  int off_h, off_w, dir;        // A box origin shift of tap (r,s): (off_h + dir*r, off_w + dir*s)
+  int8_t tap_dh[25], tap_dw[25];  // A box origin shift of k-loop tap i (rows / columns of the A pixel grid)
+  int8_t tap_par[25];           // stride-2 forward: which (row parity*2 + column parity) plane of x the tap reads
+  int8_t tap_w[25];             // weight tap (r*S+s) the k-loop tap i multiplies with
+  int a5d;                      // A maps are 5-D stride-2 views {2C, W/2, 2, H/2, N} of x (forward / wgrad of stride 2)
+  int par_c;                    // ... channel offset of the odd-column plane (= Cin)
+  int oH, oW, os, ooh, oow;     // output pixel of tile pixel (n,h,w): (n, h*os + ooh, w*os + oow) in an oH x oW image
   int nchunk1, nchunk2;         // 32-channel chunks of source 1 / source 2
   int k2_base;                  // K index of source 2's first channel inside one tap (= Cin)
   int bk_tap, br_tap;           // B box origin of tap t: (t*bk_tap + k, t*br_tap + n0)
@@ -300,7 +312,7 @@ __device__ __forceinline__ RowCtx row_ctx(const TcParams& p, int mt, int row) {
     const int in = row / per_img, rem = row - in * per_img;
     const int ih = rem / p.tw, iw = rem - ih * p.tw;
     r.ok = row < per_img * p.tn && (n0 + in) < p.N && (h0 + ih) < p.H;
-    r.base = ((int64_t)(n0 + in) * p.H + (h0 + ih)) * p.W + iw;
+    r.base = ((int64_t)(n0 + in) * p.oH + (h0 + ih) * p.os + p.ooh) * p.oW + iw * p.os + p.oow;
   } else {
     const int nch = p.nchunk1 + p.nchunk2;
     const int job = mt * 4 + (row >> 5);
@@ -415,8 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint32_t tx = (uint32_t)(p.tw * p.th * p.tn) * 128u + p.b_bytes;
           int tap = ka / nch, c = ka - tap * nch;
           for (int k = ka; k < kb; ++k, ++it) {
-            const int r = tap / p.S, s = tap - r * p.S;
-            const int ah = h0 + p.off_h + p.dir * r, aw = p.off_w + p.dir * s;
+            const int ah = h0 + p.tap_dh[tap], aw = p.tap_dw[tap], wt = p.tap_w[tap];
             const int st = it % p.stages;
             const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
             mbar_wait(smem_u32(&ctl->empty[st]), ph ^ 1u);
@@ -424,14 +435,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t sa = stage_base + (uint32_t)st * stage_bytes;
             mbar_expect_tx(full, tx);
             int kk;
-            if (c < p.nchunk1) {
+            if (p.a5d) {
+              const int par = p.tap_par[tap];
+              tma_load_5d(sa, &maps.m[0], full, (par & 1) * p.par_c + c * kChunk, aw, par >> 1, ah, n0);
+              kk = c * kChunk;
+            } else if (c < p.nchunk1) {
               tma_load_4d(sa, &maps.m[0], full, c * kChunk, aw, ah, n0);
               kk = c * kChunk;
             } else {
               tma_load_4d(sa, &maps.m[1], full, (c - p.nchunk1) * kChunk, aw, ah, n0);
               kk = p.k2_base + (c - p.nchunk1) * kChunk;
             }
-            tma_load_2d(sa + p.a_bytes, &maps.m[2], full, tap * p.bk_tap + kk, tap * p.br_tap + nt * p.BN);
+            tma_load_2d(sa + p.a_bytes, &maps.m[2], full, wt * p.bk_tap + kk, wt * p.br_tap + nt * p.BN);
             if (++c == nch) { c = 0; ++tap; }
           }
         } else {
@@ -439,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const int nb = p.BN / kChunk;
           int njob = p.njobs - mt * 4;
           njob = njob > 4 ? 4 : njob;
-          int jc[4], jh[4], jw[4], js[4];
+          int jc[4], jh[4], jw[4], js[4], jp[4];
           for (int j = 0; j < 4; ++j) {
             const int job = mt * 4 + j;
             const int tap = job / nch, c = job - tap * nch;
@@ -447,6 +462,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             jh[j] = r - p.pad_t; jw[j] = s - p.pad_l;
             js[j] = c >= p.nchunk1;
             jc[j] = (js[j] ? c - p.nchunk1 : c) * kChunk;
+            jp[j] = 0;
+            if (p.a5d) {  // input row 2*ho + e: plane e & 1, offset e >> 1 (floor) in the half-resolution grid
+              jp[j] = jh[j] & 1;
+              jc[j] += (jw[j] & 1) * p.par_c;
+              jh[j] >>= 1; jw[j] >>= 1;
+            }
           }
           const uint32_t tx = (uint32_t)(njob + nb) * box_bytes;
           for (int k = ka; k < kb; ++k, ++it) {
@@ -459,8 +480,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t full = smem_u32(&ctl->full[st]);
             const uint32_t sa = stage_base + (uint32_t)st * stage_bytes;
             mbar_expect_tx(full, tx);
-            for (int j = 0; j < njob; ++j)
-              tma_load_4d(sa + (uint32_t)j * box_bytes, &maps.m[js[j]], full, jc[j], jw[j], h0 + jh[j], n0);
+            for (int j = 0; j < njob; ++j) {
+              if (p.a5d) tma_load_5d(sa + (uint32_t)j * box_bytes, &maps.m[0], full, jc[j], jw[j], jp[j], h0 + jh[j], n0);
+              else tma_load_4d(sa + (uint32_t)j * box_bytes, &maps.m[js[j]], full, jc[j], jw[j], h0 + jh[j], n0);
+            }
             for (int b = 0; b < nb; ++b)
               tma_load_4d(sa + p.a_bytes + (uint32_t)b * box_bytes, &maps.m[2], full, nt * p.BN + b * kChunk, 0, h0, n0);
           }
@@ -855,13 +878,52 @@ int pick_bn(int n_total, int mult, int cap) {
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-bool common_ok(const NvaeConvDesc* d) {
-  if (d->stride != 1 || d->Ho != d->H || d->Wo != d->W) return false;
-  if (d->W > 128) return false;
+// 5-D stride-2 view of an NHWC tensor (H, W even): {2C, W/2, 2, H/2, N}; coordinate 0 = column parity * C + c
+int make_map_s2(CUtensorMap* m, const float* base, int N, int H, int W, int C, int tw, int th, int tn,
+                CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return NVAE_E_DRIVER;
+  cuuint64_t dims[5] = {(cuuint64_t)2 * C, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)2 * C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)2 * W * C * 4,
+                           (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[5] = {(cuuint32_t)kChunk, (cuuint32_t)tw, 1, (cuuint32_t)th, (cuuint32_t)tn};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NVAE_OK : NVAE_E_DRIVER;
+}
+
+// Taps of a stride-2 backward-data launch for the output pixels of parity (a, b): dx[2h'+a, 2w'+b] sums
+// dy[h' + (a + pad_t - r)/2, w' + (b + pad_l - s)/2] * w[r, s] over the taps whose offsets are whole.
+struct TapList { int n; int8_t dh[25], dw[25], w[25]; };
+TapList s2_dgrad_taps(const NvaeConvDesc* d, int a, int b) {
+  TapList t{};
+  for (int r = 0; r < d->R; ++r)
+    for (int s = 0; s < d->S; ++s) {
+      const int eh = a + d->pad_t - r, ew = b + d->pad_l - s;
+      if ((eh & 1) || (ew & 1)) continue;
+      t.dh[t.n] = (int8_t)(eh / 2); t.dw[t.n] = (int8_t)(ew / 2); t.w[t.n] = (int8_t)(r * d->S + s);
+      ++t.n;
+    }
+  return t;
+}
+
+// which: 0 forward, 1 dgrad, 2 wgrad
+bool common_ok(const NvaeConvDesc* d, int which) {
+  if (d->R * d->S > 25) return false;
   if ((d->Cin & 3) || (d->Cin2 & 3) || (d->Cout & 3) || d->Cout < 8) return false;
   if (d->Cin2 > 0 && (d->Cin % kChunk) != 0) return false;
   if ((d->y_ld & 3) || (d->y_off & 3)) return false;
   if (!(d->pre_scale == 0.f && d->pre_shift == 0.f) && !(d->pre_scale == 1.f && d->pre_shift == 0.f)) return false;
+  if (d->Wo > 128) return false;
+  if (d->stride == 1) return d->Ho == d->H && d->Wo == d->W;
+  // stride 2: half-resolution parity planes of x, addressed through a 5-D tensor map
+  if (d->stride != 2 || (d->H & 1) || (d->W & 1) || d->Cin2 != 0 || (d->Cin % kChunk) != 0) return false;
+  if (d->pad_t < -1 || d->pad_l < -1) return false;
+  if (which == 1)  // every output parity class needs a tap (else its pixels would have to be zero-filled)
+    for (int ab = 0; ab < 4; ++ab)
+      if (s2_dgrad_taps(d, ab >> 1, ab & 1).n == 0) return false;
   return true;
 }
 
@@ -921,17 +983,17 @@ bool finish_plan(Plan* pl, int passes, bool wgrad) {
   return true;
 }
 
-// which: 0 forward, 1 dgrad
-bool plan_gemm(const NvaeConvDesc* d, int which, Plan* pl) {
-  if (!common_ok(d) || !pick_pix_tile(d->N, d->H, d->W, kBM, 1, &pl->t)) return false;
+// which: 0 forward, 1 dgrad; ntaps: K-loop taps (a stride-2 dgrad launch covers one output parity class)
+bool plan_gemm(const NvaeConvDesc* d, int which, int ntaps, Plan* pl) {
+  if (!common_ok(d, which) || !pick_pix_tile(d->N, d->Ho, d->Wo, kBM, 1, &pl->t)) return false;
   const int passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
-  const int Ct = d->Cin + d->Cin2, taps = d->R * d->S;
+  const int Ct = d->Cin + d->Cin2;
   const int n_total = which == 0 ? d->Cout : Ct;
   pl->BN = pick_bn(n_total, 16, passes == 3 ? 192 : 256);
   pl->n_mtiles = pl->t.n_tiles;
   pl->n_ntiles = (int)ceil_div(n_total, pl->BN);
   const int nch = which == 0 ? (int)(ceil_div(d->Cin, kChunk) + ceil_div(d->Cin2, kChunk)) : (int)ceil_div(d->Cout, kChunk);
-  pl->KU = taps * nch;
+  pl->KU = ntaps * nch;
   pl->a_bytes = kBM * 128;
   pl->b_bytes = (uint32_t)pl->BN * 128;
   pl->njobs = 0;
@@ -939,10 +1001,10 @@ bool plan_gemm(const NvaeConvDesc* d, int which, Plan* pl) {
 }
 
 bool plan_wgrad(const NvaeConvDesc* d, Plan* pl) {
-  if (!common_ok(d)) return false;
+  if (!common_ok(d, 2)) return false;
   const int passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
-  if (!pick_pix_tile(d->N, d->H, d->W, 32, 8, &pl->t) && !pick_pix_tile(d->N, d->H, d->W, 64, 8, &pl->t) &&
-      !pick_pix_tile(d->N, d->H, d->W, 128, 8, &pl->t))
+  if (!pick_pix_tile(d->N, d->Ho, d->Wo, 32, 8, &pl->t) && !pick_pix_tile(d->N, d->Ho, d->Wo, 64, 8, &pl->t) &&
+      !pick_pix_tile(d->N, d->Ho, d->Wo, 128, 8, &pl->t))
     return false;
   const int KP = pl->t.tw * pl->t.th * pl->t.tn;
   const int nch = (int)(ceil_div(d->Cin, kChunk) + ceil_div(d->Cin2, kChunk));
@@ -960,7 +1022,9 @@ bool plan_wgrad(const NvaeConvDesc* d, Plan* pl) {
 }
 
 void fill_common(TcParams* p, const NvaeConvDesc* d, const Plan& pl, float* part) {
-  p->N = d->N; p->H = d->H; p->W = d->W;
+  p->N = d->N; p->H = d->Ho; p->W = d->Wo;  // the GEMM's pixel grid (== H x W for stride 1)
+  p->oH = d->Ho; p->oW = d->Wo; p->os = 1; p->ooh = 0; p->oow = 0;
+  p->a5d = 0; p->par_c = d->Cin;
   p->tw = pl.t.tw; p->th = pl.t.th; p->tn = pl.t.tn; p->tiles_h = pl.t.tiles_h;
   p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
   p->n_ntiles = pl.n_ntiles; p->KU = pl.KU; p->U = pl.U;
@@ -995,28 +1059,53 @@ int launch(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t 
 
 bool nvae_conv_tc_supported(const NvaeConvDesc* d, int which) {
   Plan pl;
-  return which == 2 ? plan_wgrad(d, &pl) : plan_gemm(d, which, &pl);
+  if (which == 2) return plan_wgrad(d, &pl);
+  if (which == 1 && d->stride == 2) {
+    if (!common_ok(d, 1)) return false;
+    for (int ab = 0; ab < 4; ++ab)
+      if (!plan_gemm(d, 1, s2_dgrad_taps(d, ab >> 1, ab & 1).n, &pl)) return false;
+    return true;
+  }
+  return plan_gemm(d, which, d->R * d->S, &pl);
 }
 
 size_t nvae_conv_tc_ws_bytes(const NvaeConvDesc* d, int which) {
   Plan pl;
-  if (!(which == 2 ? plan_wgrad(d, &pl) : plan_gemm(d, which, &pl))) return 0;
-  return pl.part_bytes;
+  if (which == 2) return plan_wgrad(d, &pl) ? pl.part_bytes : 0;
+  if (which == 1 && d->stride == 2) {
+    size_t mx = 0;
+    if (!common_ok(d, 1)) return 0;
+    for (int ab = 0; ab < 4; ++ab)
+      if (plan_gemm(d, 1, s2_dgrad_taps(d, ab >> 1, ab & 1).n, &pl) && pl.part_bytes > mx) mx = pl.part_bytes;
+    return mx;
+  }
+  return plan_gemm(d, which, d->R * d->S, &pl) ? pl.part_bytes : 0;
 }
 
 int nvae_conv2d_fwd_tc(const NvaeConvDesc* d, const float* x, const float* x2, const float* w_tr, const float* bias,
                        const float* residual, float* y, void* ws, size_t ws_bytes, cudaStream_t stream) {
   Plan pl;
-  if (!plan_gemm(d, 0, &pl)) return NVAE_E_UNSUPPORTED;
+  const int Ct = d->Cin + d->Cin2, taps = d->R * d->S;
+  if (!plan_gemm(d, 0, taps, &pl)) return NVAE_E_UNSUPPORTED;
   if (!aligned16(x) || !aligned16(x2) || !aligned16(w_tr) || !aligned16(bias) || !aligned16(residual) || !aligned16(y) ||
       !aligned16(ws))
     return NVAE_E_UNSUPPORTED;
   if (pl.part_bytes > 0 && (ws == nullptr || ws_bytes < pl.part_bytes)) return NVAE_E_WORKSPACE;
-  const int Ct = d->Cin + d->Cin2, taps = d->R * d->S;
   TcParams p{};
   fill_common(&p, d, pl, reinterpret_cast<float*>(ws));
   p.taps = taps; p.S = d->S;
-  p.off_h = -d->pad_t; p.off_w = -d->pad_l; p.dir = 1;
+  for (int r = 0; r < d->R; ++r)
+    for (int sx = 0; sx < d->S; ++sx) {
+      const int i = r * d->S + sx, eh = r - d->pad_t, ew = sx - d->pad_l;
+      p.tap_w[i] = (int8_t)i;
+      if (d->stride == 1) {
+        p.tap_dh[i] = (int8_t)eh; p.tap_dw[i] = (int8_t)ew; p.tap_par[i] = 0;
+      } else {  // input row 2*ho + eh: parity plane eh & 1 at half-resolution offset floor(eh / 2)
+        p.tap_dh[i] = (int8_t)(eh >> 1); p.tap_dw[i] = (int8_t)(ew >> 1);
+        p.tap_par[i] = (int8_t)(((eh & 1) << 1) | (ew & 1));
+      }
+    }
+  p.a5d = d->stride == 2;
   p.nchunk1 = (d->Cin + kChunk - 1) / kChunk;
   p.nchunk2 = (d->Cin2 + kChunk - 1) / kChunk;
   p.k2_base = d->Cin;
@@ -1026,7 +1115,11 @@ int nvae_conv2d_fwd_tc(const NvaeConvDesc* d, const float* x, const float* x2, c
   p.ld1 = d->y_ld > 0 ? d->y_ld : d->Cout; p.off1 = d->y_off; p.ld2 = 0;
   p.bias = bias; p.res = residual; p.accumulate = 0;
   TmapSet maps;
-  int rc = make_map_nhwc(&maps.m[0], x, d->N, d->H, d->W, d->Cin, d->Cin, pl.t.tw, pl.t.th, pl.t.tn);
+  int rc;
+  if (d->stride == 2)
+    rc = make_map_s2(&maps.m[0], x, d->N, d->H, d->W, d->Cin, pl.t.tw, pl.t.th, pl.t.tn, CU_TENSOR_MAP_SWIZZLE_128B);
+  else
+    rc = make_map_nhwc(&maps.m[0], x, d->N, d->H, d->W, d->Cin, d->Cin, pl.t.tw, pl.t.th, pl.t.tn);
   if (rc) return rc;
   if (d->Cin2 > 0) rc = make_map_nhwc(&maps.m[1], x2, d->N, d->H, d->W, d->Cin2, d->Cin2, pl.t.tw, pl.t.th, pl.t.tn);
   else maps.m[1] = maps.m[0];
@@ -1038,33 +1131,51 @@ int nvae_conv2d_fwd_tc(const NvaeConvDesc* d, const float* x, const float* x2, c
 
 int nvae_conv2d_dgrad_tc(const NvaeConvDesc* d, const float* dy, const float* w_rnd, float* dx, float* dx2,
                          int accumulate, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  Plan pl;
-  if (!plan_gemm(d, 1, &pl)) return NVAE_E_UNSUPPORTED;
+  if (!common_ok(d, 1)) return NVAE_E_UNSUPPORTED;
   if (!aligned16(dy) || !aligned16(w_rnd) || !aligned16(dx) || !aligned16(dx2) || !aligned16(ws))
     return NVAE_E_UNSUPPORTED;
   if (dx == nullptr) return NVAE_E_UNSUPPORTED;
-  if (pl.part_bytes > 0 && (ws == nullptr || ws_bytes < pl.part_bytes)) return NVAE_E_WORKSPACE;
   const int Ct = d->Cin + d->Cin2, taps = d->R * d->S;
   const int ld = d->y_ld > 0 ? d->y_ld : d->Cout;
-  TcParams p{};
-  fill_common(&p, d, pl, reinterpret_cast<float*>(ws));
-  p.taps = taps; p.S = d->S;
-  p.off_h = d->pad_t; p.off_w = d->pad_l; p.dir = -1;  // dx[h,w] = sum dy[h + pad_t - r, w + pad_l - s] * w[r,s]
-  p.nchunk1 = (d->Cout + kChunk - 1) / kChunk;
-  p.nchunk2 = 0;
-  p.k2_base = 0;
-  p.bk_tap = 0; p.br_tap = Ct;
-  p.n_valid = Ct; p.n_split = d->Cin;
-  p.out1 = dx; p.out2 = dx2;
-  p.ld1 = d->Cin; p.off1 = 0; p.ld2 = d->Cin2;
-  p.bias = nullptr; p.res = nullptr; p.accumulate = accumulate;
-  TmapSet maps;
-  int rc = make_map_nhwc(&maps.m[0], dy + d->y_off, d->N, d->H, d->W, d->Cout, ld, pl.t.tw, pl.t.th, pl.t.tn);
-  if (rc) return rc;
-  maps.m[1] = maps.m[0];
-  rc = make_map_2d(&maps.m[2], w_rnd, (int64_t)taps * Ct, d->Cout, pl.BN);
-  if (rc) return rc;
-  return launch<false>(maps, p, pl, stream);
+  const int nclass = d->stride == 2 ? 4 : 1;
+  for (int ab = 0; ab < nclass; ++ab) {
+    TapList tl{};
+    if (d->stride == 2) {
+      tl = s2_dgrad_taps(d, ab >> 1, ab & 1);
+    } else {  // dx[h,w] = sum dy[h + pad_t - r, w + pad_l - s] * w[r,s]
+      tl.n = taps;
+      for (int r = 0; r < d->R; ++r)
+        for (int sx = 0; sx < d->S; ++sx) {
+          const int i = r * d->S + sx;
+          tl.dh[i] = (int8_t)(d->pad_t - r); tl.dw[i] = (int8_t)(d->pad_l - sx); tl.w[i] = (int8_t)i;
+        }
+    }
+    Plan pl;
+    if (!plan_gemm(d, 1, tl.n, &pl)) return NVAE_E_UNSUPPORTED;
+    if (pl.part_bytes > 0 && (ws == nullptr || ws_bytes < pl.part_bytes)) return NVAE_E_WORKSPACE;
+    TcParams p{};
+    fill_common(&p, d, pl, reinterpret_cast<float*>(ws));
+    p.taps = tl.n; p.S = d->S;
+    for (int i = 0; i < tl.n; ++i) { p.tap_dh[i] = tl.dh[i]; p.tap_dw[i] = tl.dw[i]; p.tap_w[i] = tl.w[i]; p.tap_par[i] = 0; }
+    if (d->stride == 2) { p.oH = d->H; p.oW = d->W; p.os = 2; p.ooh = ab >> 1; p.oow = ab & 1; }
+    p.nchunk1 = (d->Cout + kChunk - 1) / kChunk;
+    p.nchunk2 = 0;
+    p.k2_base = 0;
+    p.bk_tap = 0; p.br_tap = Ct;
+    p.n_valid = Ct; p.n_split = d->Cin;
+    p.out1 = dx; p.out2 = dx2;
+    p.ld1 = d->Cin; p.off1 = 0; p.ld2 = d->Cin2;
+    p.bias = nullptr; p.res = nullptr; p.accumulate = accumulate;
+    TmapSet maps;
+    int rc = make_map_nhwc(&maps.m[0], dy + d->y_off, d->N, d->Ho, d->Wo, d->Cout, ld, pl.t.tw, pl.t.th, pl.t.tn);
+    if (rc) return rc;
+    maps.m[1] = maps.m[0];
+    rc = make_map_2d(&maps.m[2], w_rnd, (int64_t)taps * Ct, d->Cout, pl.BN);
+    if (rc) return rc;
+    rc = launch<false>(maps, p, pl, stream);
+    if (rc) return rc;
+  }
+  return NVAE_OK;
 }
 
 int nvae_conv2d_wgrad_tc(const NvaeConvDesc* d, const float* x, const float* x2, const float* dy, float* dw, void* ws,
@@ -1084,14 +1195,17 @@ int nvae_conv2d_wgrad_tc(const NvaeConvDesc* d, const float* x, const float* x2,
   p.njobs = pl.njobs;
   p.Cin = d->Cin; p.Cin2 = d->Cin2; p.Ct = Ct; p.Cout = d->Cout;
   p.out1 = dw;
+  p.a5d = d->stride == 2;
   TmapSet maps;
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  int rc = make_map_nhwc(&maps.m[0], x, d->N, d->H, d->W, d->Cin, d->Cin, p.tw, p.th, p.tn, swz);
+  int rc;
+  if (d->stride == 2) rc = make_map_s2(&maps.m[0], x, d->N, d->H, d->W, d->Cin, p.tw, p.th, p.tn, swz);
+  else rc = make_map_nhwc(&maps.m[0], x, d->N, d->H, d->W, d->Cin, d->Cin, p.tw, p.th, p.tn, swz);
   if (rc) return rc;
   if (d->Cin2 > 0) rc = make_map_nhwc(&maps.m[1], x2, d->N, d->H, d->W, d->Cin2, d->Cin2, p.tw, p.th, p.tn, swz);
   else maps.m[1] = maps.m[0];
   if (rc) return rc;
-  rc = make_map_nhwc(&maps.m[2], dy + d->y_off, d->N, d->H, d->W, d->Cout, ld, p.tw, p.th, p.tn, swz);
+  rc = make_map_nhwc(&maps.m[2], dy + d->y_off, d->N, d->Ho, d->Wo, d->Cout, ld, p.tw, p.th, p.tn, swz);
   if (rc) return rc;
   return launch<true>(maps, p, pl, stream);
 }

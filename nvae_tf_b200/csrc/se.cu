@@ -147,30 +147,41 @@ __global__ void __launch_bounds__(kSeThreads) se_bwd_gate_kernel(
   }
 }
 
-// dense-layer gradients: fixed-order sums over the batch (deterministic)
+// dense-layer gradients: fixed-order sums over the batch (deterministic).  Four interleaved partial sums per
+// output so four pairs of loads are in flight (a single dependent chain made this kernel latency-bound).
+__device__ __forceinline__ float se_dot_batch(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                              int B) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int i = 0;
+  for (; i + 3 < B; i += 4) {
+    const float a0 = __ldg(a + (int64_t)i * lda), a1 = __ldg(a + (int64_t)(i + 1) * lda),
+                a2 = __ldg(a + (int64_t)(i + 2) * lda), a3 = __ldg(a + (int64_t)(i + 3) * lda);
+    const float b0 = b ? __ldg(b + (int64_t)i * ldb) : 1.f, b1 = b ? __ldg(b + (int64_t)(i + 1) * ldb) : 1.f,
+                b2 = b ? __ldg(b + (int64_t)(i + 2) * ldb) : 1.f, b3 = b ? __ldg(b + (int64_t)(i + 3) * ldb) : 1.f;
+    s0 = fmaf(a0, b0, s0); s1 = fmaf(a1, b1, s1); s2 = fmaf(a2, b2, s2); s3 = fmaf(a3, b3, s3);
+  }
+  for (; i < B; ++i) s0 = fmaf(__ldg(a + (int64_t)i * lda), b ? __ldg(b + (int64_t)i * ldb) : 1.f, s0);
+  return (s0 + s1) + (s2 + s3);
+}
+
 __global__ void se_bwd_weights_kernel(const float* __restrict__ pooled, const float* __restrict__ hidden,
                                       const float* __restrict__ dz2, const float* __restrict__ dh, int B, int C,
                                       int hid, float* __restrict__ dw1, float* __restrict__ db1,
                                       float* __restrict__ dw2, float* __restrict__ db2) {
   const int n1 = C * hid, total = 2 * n1 + C + hid;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    float s = 0.f;
     if (i < n1) {  // dw2[j][c]
       const int j = i / C, c = i % C;
-      for (int b = 0; b < B; ++b) s = fmaf(hidden[(int64_t)b * hid + j], dz2[(int64_t)b * C + c], s);
-      dw2[i] = s;
+      dw2[i] = se_dot_batch(hidden + j, hid, dz2 + c, C, B);
     } else if (i < 2 * n1) {  // dw1[c][j]
       const int k = i - n1, c = k / hid, j = k % hid;
-      for (int b = 0; b < B; ++b) s = fmaf(pooled[(int64_t)b * C + c], dh[(int64_t)b * hid + j], s);
-      dw1[k] = s;
+      dw1[k] = se_dot_batch(pooled + c, C, dh + j, hid, B);
     } else if (i < 2 * n1 + C) {
       const int c = i - 2 * n1;
-      for (int b = 0; b < B; ++b) s += dz2[(int64_t)b * C + c];
-      db2[c] = s;
+      db2[c] = se_dot_batch(dz2 + c, C, nullptr, 0, B);
     } else {
       const int j = i - 2 * n1 - C;
-      for (int b = 0; b < B; ++b) s += dh[(int64_t)b * hid + j];
-      db1[j] = s;
+      db1[j] = se_dot_batch(dh + j, hid, nullptr, 0, B);
     }
   }
 }

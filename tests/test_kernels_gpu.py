@@ -159,6 +159,56 @@ TC_CASES = [
     (2, 32, 32, 32, 0, 32, 3, False),     # W*th tile with two image rows per box
 ]
 
+S2_CASES = [
+    # (N, H, W, Cin, Cout, k, shift, tensor-core directions [fwd, dgrad, wgrad])
+    (3, 8, 8, 32, 64, 3, (0, 0), [1, 1, 1]),      # Rescaler DOWN / BNSwishConv stride 2 (common.py:155-163)
+    (2, 16, 16, 64, 128, 3, (0, 0), [1, 1, 1]),
+    (5, 8, 8, 128, 256, 3, (0, 0), [1, 1, 1]),    # encoder Rescaler at the model's shape
+    (2, 8, 8, 32, 16, 1, (0, 0), [1, 0, 1]),      # SkipScaler 1x1 stride 2 (preprocess.py:46-63); dgrad: 3 of 4
+    (2, 8, 8, 32, 16, 1, (1, 1), [1, 0, 1]),      # parity classes have no tap -> fp32 CUDA-core path
+    (2, 8, 8, 32, 16, 1, (0, 1), [1, 0, 1]),
+    (2, 8, 8, 64, 32, 1, (1, 0), [1, 0, 1]),
+]
+
+
+@pytest.mark.parametrize("case", S2_CASES)
+def test_conv2d_stride2_tensor_core(lib_built, case):
+    """Stride-2 convolutions on tcgen05: x is read through a 5-D TMA view of its four parity planes; backward-data
+    runs as four launches, one per output-pixel parity class."""
+    import ctypes as C
+    from nvae_tf_b200 import _lib
+    from nvae_tf_b200 import runtime as R
+    from nvae_tf_b200.layers import Conv2D
+    N, Hh, W, Cin, Cout, k, shift, want_tc = case
+    rng = np.random.default_rng(6)
+    with R.Runtime(seed=7, precision=_lib.NVAE_PREC_TF32X3) as rt:
+        conv = Conv2D(Cout, (k, k), strides=(2, 2), padding="same", in_channels=Cin, name="c")
+        rt.finalize()
+        w = f32(rng.normal(0, 1.0 / np.sqrt(k * k * Cin), (k, k, Cin, Cout)))
+        b = f32(rng.normal(0, 0.3, Cout))
+        conv.kernel.assign(w)
+        conv.bias.assign(b)
+        x = f32(rng.normal(0, 1, (N, Hh, W, Cin)))
+        xo = H.t64(x).requires_grad_(True)
+        wo, bo = H.t64(w).requires_grad_(True), H.t64(b).requires_grad_(True)
+        yo = O.conv2d(xo[:, shift[0]:, shift[1]:, :], wo, bo, 2)
+        dy = f32(rng.normal(0, 1, tuple(yo.shape)))
+        yo.backward(H.t64(dy))
+        xt = dev(rt, x)
+        d = R.conv_desc(rt, xt.shape, 0, conv.kernel.shape, 2, shift)
+        got_tc = [rt.lib._nvae_conv2d_uses_tensor_cores(C.byref(d), i) for i in range(3)]
+        assert got_tc == want_tc, got_tc
+        with rt.gradient_tape() as tape:
+            y = conv(xt, shift=shift)
+        assert y.shape == tuple(yo.shape)
+        seed_grad(rt, y, dy)
+        rt.backward(tape)
+        check("y", npy(y.data), yo.detach().numpy())
+        check("dx", npy(xt.grad), xo.grad.numpy())
+        check("dw", npy(conv.kernel.grad), wo.grad.numpy())
+        check("db", npy(conv.bias.grad), bo.grad.numpy())
+
+
 
 @pytest.mark.parametrize("mode,tol", [("tf32x3", 2e-5), ("tf32", 3e-3)])
 @pytest.mark.parametrize("case", TC_CASES)
