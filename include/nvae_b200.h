@@ -51,6 +51,9 @@ enum { NVAE_PREC_FP32 = 0, NVAE_PREC_TF32 = 1, NVAE_PREC_TF32X3 = 2 };
 
 /* Library / device identification. Returns 100 for sm_100; build id string is static. */
 NVAE_API int nvae_version(void);
+/* Kernels launched by this library since it was loaded (host-side counter; launches recorded into a CUDA graph
+ * count once, at capture).  bench.py derives `gpu_launches` from it. */
+NVAE_API uint64_t nvae_launch_count(void);
 NVAE_API const char* nvae_build_info(void);
 
 /* ------------------------------------------------------------------------------------------

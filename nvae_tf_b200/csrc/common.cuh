@@ -5,8 +5,11 @@
 
 #include "../../include/nvae_b200.h"
 
+// every kernel launch in the library is followed by this macro: it also counts the launch (nvae_launch_count)
+extern unsigned long long nvae_launch_counter;
 #define NVAE_RETURN_IF_LAUNCH_FAILED()                 \
   do {                                                 \
+    ++nvae_launch_counter;                             \
     cudaError_t e__ = cudaGetLastError();              \
     if (e__ != cudaSuccess) return (int)e__;           \
   } while (0)

@@ -130,6 +130,8 @@ static int grid_for(int64_t n, int threads) {
 
 using namespace nvae;
 
+unsigned long long nvae_launch_counter = 0;
+extern "C" uint64_t nvae_launch_count(void) { return (uint64_t)nvae_launch_counter; }
 extern "C" int nvae_version(void) { return 100; }
 extern "C" const char* nvae_build_info(void) { return "libnvae_b200 sm_100a (tcgen05/TMA) built " __DATE__ " " __TIME__; }
 

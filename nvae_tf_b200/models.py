@@ -246,9 +246,10 @@ class NVAE:
         torch.cuda.synchronize(rt.device)
         self._sync_counters()
         graph = torch.cuda.CUDAGraph()
-        launches0 = rt.lib.launches
+        launches0, kernels0 = rt.lib.launches, rt.lib._nvae_launch_count()
         with torch.cuda.graph(graph, stream=stream):
             out = self.train_step(static_in, apply_gradients=in_graph)
+        self.graph_kernels = rt.lib._nvae_launch_count() - kernels0 + (0 if in_graph else 1)  # + Adamax outside
         self.steps -= 1  # capture records the launches without running them
         self._host_metric = self.steps if self.step_based_warmup else self.epoch
         self.graph_launches = rt.lib.launches - launches0 + (0 if in_graph else 1)

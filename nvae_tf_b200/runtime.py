@@ -111,7 +111,14 @@ class Runtime:
         self._scope: List[str] = []
         self.tape: Optional[List[Callable[[], None]]] = None
         self.params = self.grads = self.state = None
-        self.ws: Optional[torch.Tensor] = None
+        self._ws: Dict[str, torch.Tensor] = {}
+        self._side: Optional[torch.cuda.Stream] = None
+        self._on_side = False
+        self._side_dirty = False
+        self._keepalive: List[torch.Tensor] = []
+        # single-pass TF32 rounds gradients in place before use, which a concurrent reader must not see half-done
+        self.use_side_stream = (os.environ.get("NVAE_WGRAD_STREAM", "1") != "0" and
+                                self.precision != _lib.NVAE_PREC_TF32 and self.device.type == "cuda")
         self.sn_done = False
         self.eps_injected: Optional[List[torch.Tensor]] = None
         self.eps_i = 0
@@ -216,12 +223,51 @@ class Runtime:
         return t
 
     def workspace(self, nbytes: int) -> Tuple[int, int]:
+        """Scratch for the launch being issued on the CURRENT stream (one buffer per stream: kernels on the
+        weight-gradient side stream must not share scratch with the main stream's)."""
         nbytes = int(nbytes)
-        if self.ws is None or self.ws.numel() < nbytes:
+        key = "side" if self._on_side else "main"
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
             if torch.cuda.is_current_stream_capturing():
                 raise _lib.NvaeError("workspace must be sized by an eager warm-up step before graph capture")
-            self.ws = torch.empty(max(nbytes, 32 << 20), dtype=torch.uint8, device=self.device)
-        return self.ws.data_ptr(), self.ws.numel()
+            torch.cuda.synchronize(self.device)  # nothing in flight may still be using the old buffer
+            ws = self._ws[key] = torch.empty(max(nbytes, 32 << 20), dtype=torch.uint8, device=self.device)
+        return ws.data_ptr(), ws.numel()
+
+    # ---- weight-gradient side stream ------------------------------------------------------------------
+    @contextmanager
+    def side_stream(self):
+        """Runs the enclosed launches (backward-filter + bias-gradient of one conv) on a second stream that waits
+        for everything issued so far on the current one.  Independent of the rest of backward (they only write the
+        gradient arena), these mostly small, latency-bound kernels then overlap the dgrad / BN-backward chain.
+        Works eagerly and under CUDA-graph capture (fork/join become graph edges).  `join_side_stream` must run
+        before anything reads the gradient arena."""
+        if not self.use_side_stream:
+            yield
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._side.wait_stream(main)
+        self._on_side = True
+        try:
+            with torch.cuda.stream(self._side):
+                yield
+        finally:
+            self._on_side = False
+            self._side_dirty = True
+
+    def keep_alive(self, t) -> None:
+        """Holds a reference to a buffer a side-stream launch reads until the streams are joined."""
+        if self.use_side_stream:
+            self._keepalive.append(t)
+
+    def join_side_stream(self) -> None:
+        if self._side_dirty:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._side_dirty = False
+        self._keepalive.clear()
 
     def tensor(self, data: torch.Tensor, needs_grad: bool = True) -> DeviceTensor:
         return DeviceTensor(data, needs_grad)
@@ -267,6 +313,7 @@ class Runtime:
     def backward(self, tape: List[Callable[[], None]]) -> None:
         for fn in reversed(tape):
             fn()
+        self.join_side_stream()
         tape.clear()
 
     # ---- epsilon source (common.py:67) -----------------------------------------------------------
@@ -512,9 +559,11 @@ def conv2d(rt: Runtime, x: DeviceTensor, conv, x2: Optional[DeviceTensor] = None
                 raise RuntimeError(f"conv {k.name}: output has no gradient")
             if rt.tf32_round != "none" and (tc[1] or tc[2]):
                 rt.lib.round_tf32(dy.data_ptr(), dy.numel(), rt.stream)
-            ws, wsb = rt.workspace(rt.lib._nvae_conv2d_ws_bytes(C.byref(d), 2))
-            rt.lib.conv2d_wgrad(C.byref(d), x.ptr(), x2.ptr() if x2 is not None else None, dy.data_ptr(), k.gptr(),
-                                bias.gptr() if bias is not None else None, ws, wsb, rt.stream)
+            with rt.side_stream():
+                ws, wsb = rt.workspace(rt.lib._nvae_conv2d_ws_bytes(C.byref(d), 2))
+                rt.lib.conv2d_wgrad(C.byref(d), x.ptr(), x2.ptr() if x2 is not None else None, dy.data_ptr(),
+                                    k.gptr(), bias.gptr() if bias is not None else None, ws, wsb, rt.stream)
+            rt.keep_alive(dy)
             need1, need2 = x.needs_grad, x2 is not None and x2.needs_grad
             if need1 or need2:
                 if not need1 or (x2 is not None and not need2):
@@ -551,9 +600,12 @@ def dwconv_bn_act(rt: Runtime, x: DeviceTensor, bn, act: int, dw, training: bool
             dy = y.grad
             da = rt.empty(N, H, W, Cc)
             rt.lib.dwconv5x5_bwd_data(dy.data_ptr(), N, H, W, Cc, dw.depthwise_kernel.ptr(), da.data_ptr(), rt.stream)
-            ws, wsb = rt.workspace(rt.lib._nvae_dwconv5x5_bwd_filter_ws_bytes(N, H, W, Cc))
-            rt.lib.dwconv5x5_bwd_filter(x.ptr(), stat.data_ptr(), act, dy.data_ptr(), N, H, W, Cc,
-                                        dw.depthwise_kernel.gptr(), dw.bias.gptr(), ws, wsb, rt.stream)
+            with rt.side_stream():
+                ws, wsb = rt.workspace(rt.lib._nvae_dwconv5x5_bwd_filter_ws_bytes(N, H, W, Cc))
+                rt.lib.dwconv5x5_bwd_filter(x.ptr(), stat.data_ptr(), act, dy.data_ptr(), N, H, W, Cc,
+                                            dw.depthwise_kernel.gptr(), dw.bias.gptr(), ws, wsb, rt.stream)
+            rt.keep_alive(dy)
+            rt.keep_alive(stat)
             _bn_backward(rt, da, x, stat, bn, act, (0, 0), training)
             y.grad = None
         rt.record(bwd)

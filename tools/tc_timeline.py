@@ -42,6 +42,15 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         print(f"event time {e0.elapsed_time(e1) * 1e3:.1f} us (incl. fix-up)")
+        if os.environ.get("TC_PROFILE"):
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+            for e in prof.events():
+                if e.device_type == torch.autograd.DeviceType.CUDA:
+                    print(f"   {e.device_time:8.1f} us  {e.name[:90]}")
         if not hasattr(rt.lib.dll, "nvae_debug_tc_timing"):
             return  # regular build: timing only (this script doubles as the single-kernel workload for ncu)
         buf = (C.c_ulonglong * (148 * 16))()
