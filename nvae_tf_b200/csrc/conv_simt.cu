@@ -266,8 +266,59 @@ int nvae_colsum(const float* a, int64_t rows, int C, int ld, float* out, void* w
 
 size_t nvae_colsum_ws_bytes(int C) { return (size_t)256 * C * sizeof(float); }
 
+// Cout == 1 head (postprocess.py:29): y[pix] = b + sum_{tap,c} x[pix+tap][c] * w[tap][c].  Bandwidth-shaped, not
+// GEMM-shaped: 8 lanes share a pixel (coalesced 128-byte channel rows), taps come from L1, a 3-step shuffle sums them.
+__global__ void __launch_bounds__(256) conv_head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y, int N,
+                                                            int H, int W, int C, int R, int S, int pad_t, int pad_l) {
+  extern __shared__ float wsm[];  // [R*S][C]
+  for (int i = threadIdx.x; i < R * S * C; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  const int lane8 = threadIdx.x & 7;
+  const int64_t npix = (int64_t)N * H * W;
+  const float b = bias ? bias[0] : 0.f;
+  for (int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); pix < npix;
+       pix += (int64_t)gridDim.x * (blockDim.x >> 3)) {
+    const int wq = (int)(pix % W);
+    const int64_t t = pix / W;
+    const int hq = (int)(t % H);
+    const int64_t n = t / H;
+    float acc = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const int h = hq + r - pad_t;
+      if (h < 0 || h >= H) continue;
+      for (int s2 = 0; s2 < S; ++s2) {
+        const int ww = wq + s2 - pad_l;
+        if (ww < 0 || ww >= W) continue;
+        const float* xp = x + ((n * H + h) * W + ww) * C;
+        const float* wp = wsm + (r * S + s2) * C;
+        for (int c = lane8 * 4; c < C; c += 32) {
+          const float4 v = ldg4(xp + c);
+          const float4 k = *reinterpret_cast<const float4*>(wp + c);
+          acc = fmaf(v.x, k.x, acc); acc = fmaf(v.y, k.y, acc); acc = fmaf(v.z, k.z, acc); acc = fmaf(v.w, k.w, acc);
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (lane8 == 0) y[pix] = acc + b;
+  }
+}
+
 int nvae_conv2d_fwd_simt(const NvaeConvDesc* d, const float* x, const float* x2, const float* w, const float* bias,
                          const float* residual, float* y, cudaStream_t stream) {
+  if (d->Cout == 1 && d->stride == 1 && d->Cin2 == 0 && (d->Cin & 3) == 0 && residual == nullptr && d->y_ld <= 1 &&
+      d->y_off == 0 && (d->pre_scale == 0.f || d->pre_scale == 1.f) && d->pre_shift == 0.f && d->R * d->S * d->Cin <= 8192 &&
+      (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+    const int64_t npix = (int64_t)d->N * d->H * d->W;
+    int64_t grid = ceil_div(npix, 32);
+    if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+    conv_head_fwd_kernel<<<(int)grid, 256, (size_t)d->R * d->S * d->Cin * sizeof(float), stream>>>(
+        x, w, bias, y, d->N, d->H, d->W, d->Cin, d->R, d->S, d->pad_t, d->pad_l);
+    NVAE_RETURN_IF_LAUNCH_FAILED();
+    return NVAE_OK;
+  }
   FwdProb p;
   p.g = make_geom(d);
   p.x = x; p.x2 = x2; p.w = w; p.bias = bias; p.res = residual; p.y = y;

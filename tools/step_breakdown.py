@@ -29,14 +29,20 @@ def main():
         m.train_step(x)
         torch.cuda.synchronize()
     agg = defaultdict(lambda: [0, 0.0, 0.0])
-    for e in prof.events():
-        if e.device_type == torch.autograd.DeviceType.CUDA:
-            a = agg[e.name[:100]]
-            a[0] += 1
-            a[1] += e.device_time
-            a[2] = max(a[2], e.device_time)
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    t_lo = min(e.time_range.start for e in evs)
+    t_hi = max(e.time_range.end for e in evs)
+    per_stream = defaultdict(float)
+    for e in evs:
+        a = agg[e.name[:100]]
+        a[0] += 1
+        a[1] += e.device_time
+        a[2] = max(a[2], e.device_time)
+        per_stream[getattr(e, "device_resource_id", getattr(e, "device_index", 0))] += e.device_time
     tot = sum(a[1] for a in agg.values())
-    print(f"batch {B}: {sum(a[0] for a in agg.values())} kernels, {tot / 1e3:.2f} ms summed device time")
+    print(f"batch {B}: {sum(a[0] for a in agg.values())} kernels, {tot / 1e3:.2f} ms summed device time, "
+          f"{(t_hi - t_lo) / 1e3:.2f} ms first-start to last-end (eager, incl. launch gaps); per stream: "
+          + ", ".join(f"{k}: {v / 1e3:.2f} ms" for k, v in sorted(per_stream.items())))
     for name, (n, t, mx) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{t / 1e3:9.3f} ms {100 * t / tot:5.1f}%  n={n:5d}  avg {t / n:8.1f} us  max {mx:8.1f} us  {name}")
 
