@@ -431,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int st = it % p.stages;
             const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
             mbar_wait(smem_u32(&ctl->empty[st]), ph ^ 1u);
+            if (it == 8) TC_STAMP(7);
             const uint32_t full = smem_u32(&ctl->full[st]);
             const uint32_t sa = stage_base + (uint32_t)st * stage_bytes;
             mbar_expect_tx(full, tx);

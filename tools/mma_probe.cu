@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int mode, int niter, int 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (threadIdx.x < 32) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -92,6 +92,29 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int mode, int niter, int 
                          ::"r"(tmem), "l"(aa), "l"(bb), "r"(idesc5), "r"(it + pass + j) : "memory");
           }
       }
+    } else if (mode == 6 || mode == 7) {
+      // mode 6: as mode 5 but A (hi and lo) is read from TMEM columns 384.. (the product kernel's layout)
+      // mode 7: mode 6 + a tcgen05.commit per k-unit onto a ring of 2 mbarriers, waiting for the commit of two units ago
+      const uint32_t raw = 16384u + (uint32_t)N * 128u;
+      const uint32_t idesc5 = idesc_tf32(128, N, 0, 0);
+      __shared__ uint64_t ring[2];
+      if (mode == 7) { mbar_init(smem_u32(&ring[0]), 1); mbar_init(smem_u32(&ring[1]), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+      for (int it = 0; it < niter / 12; ++it) {
+        const uint32_t s0 = base + (uint32_t)(it % 2) * 2u * raw;
+        const uint64_t b = desc_sw128(s0 + 16384, 16, 1024, 2);
+        const uint64_t lo = raw >> 4;
+        const uint32_t a_hi = tmem + 256u + (uint32_t)(it % 2) * 64u, a_lo = a_hi + 32u;
+        if (mode == 7 && it >= 2) { while (!mbar_try_wait(smem_u32(&ring[it & 1]), (uint32_t)((it - 2) >> 1) & 1u)) {} }
+        for (int pass = 0; pass < 3; ++pass)
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t aa = (pass == 2 ? a_lo : a_hi) + 8u * j;
+            const uint64_t bb = b + (pass == 1 ? lo : 0) + 2 * j;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                         ::"r"(tmem), "r"(aa), "l"(bb), "r"(idesc5), "r"(it + pass + j) : "memory");
+          }
+        if (mode == 7)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&ring[it & 1])) : "memory");
+      }
     } else
     for (int it = 0; it < niter; ++it) {
       const uint64_t k = (uint64_t)(2 * (it & 3));
@@ -126,7 +149,7 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int mode, int niter, int 
   __syncthreads();
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
 
@@ -135,10 +158,10 @@ int main() {
   cudaMalloc(&d, 16);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int niter = 4092 * 16;
-  const char* names[6] = {"tf32 K-major SW128", "tf32 MN-major     ", "bf16 K-major SW128", "tf32 K-major SW32 ", "tf32 K-major SW64 ", "tf32 3x pattern   "};
-  for (int mode : {0, 1, 5})
-    for (int N : {32, 64, 128, 192}) {
-      for (int hammer : {0, 2}) {
+  const char* names[8] = {"tf32 K-major SW128", "tf32 MN-major     ", "bf16 K-major SW128", "tf32 K-major SW32 ", "tf32 K-major SW64 ", "tf32 3x pattern   ", "3x, A from TMEM   ", "3x TMEM-A + commit"};
+  for (int mode : {5, 6, 7})
+    for (int N : {64, 128, 192}) {
+      for (int hammer : {0, 1}) {
         const int grid = 148;
         probe<<<grid, 128, 200 * 1024>>>(N, mode, niter, hammer, d);
         cudaError_t e = cudaDeviceSynchronize();

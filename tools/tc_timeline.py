@@ -59,7 +59,7 @@ def main():
         t = t[t[:, 0] > 0]
         t0 = t[:, 0].min()
         t = (t - t0) / 1e3
-        names = ["start", "setup", "tile0", "mma_issued", "acc_done", "epi_done", "exit", "-", "cv8 begin", "cv8 lo_empty", "cv8 full",
+        names = ["start", "setup", "tile0", "mma_issued", "acc_done", "epi_done", "exit", "tma8 issue", "cv8 begin", "cv8 lo_empty", "cv8 full",
                  "cv8 converted", "cv8 arrived", "cv9 arrived", "mma8 conv ok", "mma9 conv ok"]
         print(f"rc={rc} event time {e0.elapsed_time(e1) * 1e3:.1f} us (incl. fix-up), {len(t)} CTAs; us since first CTA start:")
         for i, n in enumerate(names):
