@@ -30,14 +30,16 @@ __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return ceil_
 // ---- activations -------------------------------------------------------------
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float u) {
-  if (ACT == NVAE_ACT_SWISH) return u / (1.f + expf(-u));
+  // ex2.approx + rcp.rn: ~1e-6 relative on the swish value, a quarter of the instructions of expf + IEEE divide
+  // (the bandwidth-bound kernels that apply it are otherwise instruction-issue-bound)
+  if (ACT == NVAE_ACT_SWISH) return u * __frcp_rn(1.f + __expf(-u));
   if (ACT == NVAE_ACT_ELU) return u > 0.f ? u : expm1f(u);
   return u;
 }
 template <int ACT>
 __device__ __forceinline__ float act_grad(float u) {
   if (ACT == NVAE_ACT_SWISH) {
-    float s = 1.f / (1.f + expf(-u));
+    const float s = __frcp_rn(1.f + __expf(-u));
     return s * (1.f + u * (1.f - s));
   }
   if (ACT == NVAE_ACT_ELU) return u > 0.f ? 1.f : expf(u);

@@ -79,60 +79,67 @@ __device__ __forceinline__ void dw_stage(float* tile, const float* __restrict__ 
 }
 
 // FLIP=false: y = dwconv(act(bn(x))) + bias.   FLIP=true: da = dwconv_transpose(dy) (no prologue, no bias)
+// Compute mapping: a warp is the 32 channels of the chunk at one work item, a thread is ONE channel: its 25 taps
+// live in registers, shared-memory reads and global stores are 128-byte rows (conflict-free, fully coalesced),
+// and each thread produces a 2 x 4 output patch from a 6 x 8 input window (0.24 shared loads per FMA).
 template <bool FLIP>
-__global__ void __launch_bounds__(kDwThreads, 2) dwconv5x5_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(kDwThreads, 3) dwconv5x5_kernel(const float* __restrict__ x,
                                                                   const float* __restrict__ stat, int act, int N, int H,
                                                                   int W, int C, const float* __restrict__ wts,
                                                                   const float* __restrict__ bias, float* __restrict__ y,
                                                                   int imgs, int WQ, int PH, int PW) {
   extern __shared__ __align__(16) float smem[];
-  float* wsm = smem;             // [25][32]
-  float* tile = smem + 25 * kDwCC;
+  float* tile = smem;
   const int c0 = blockIdx.x * kDwCC, n0 = blockIdx.y * imgs;
   const int nimg = (N - n0) < imgs ? (N - n0) : imgs;
-  for (int i = threadIdx.x; i < 25 * kDwCC; i += kDwThreads) {
-    const int tap = i / kDwCC, c = i % kDwCC;
-    wsm[i] = __ldg(wts + (int64_t)(FLIP ? 24 - tap : tap) * C + c0 + c);
-  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float wreg[25];
+#pragma unroll
+  for (int t = 0; t < 25; ++t) wreg[t] = __ldg(wts + (int64_t)(FLIP ? 24 - t : t) * C + c0 + lane);
+  const float bv = (!FLIP && bias != nullptr) ? __ldg(bias + c0 + lane) : 0.f;
   dw_stage<!FLIP>(tile, x, stat, act, n0, nimg, H, W, C, c0, PH, PW);
-  const int c4 = threadIdx.x & 7;
-  float4 bv = make_float4(0, 0, 0, 0);
-  if (!FLIP && bias != nullptr) bv = ldg4(bias + c0 + c4 * 4);
-  const int items = nimg * H * WQ;
-  for (int it = threadIdx.x >> 3; it < items; it += kDwThreads >> 3) {
-    const int wq = it % WQ, t = it / WQ, h = t % H, im = t / H;
-    const int w0 = wq * kDwTW;
-    float4 acc[kDwTW];
+  const int HP = (H + 1) >> 1;
+  const int items = nimg * HP * WQ;
+  for (int it = warp; it < items; it += kDwThreads / 32) {
+    const int wq = it % WQ, t = it / WQ, hp = t % HP, im = t / HP;
+    const int h0 = hp * 2, w0 = wq * kDwTW;
+    float acc[2][kDwTW];
 #pragma unroll
-    for (int j = 0; j < kDwTW; ++j) acc[j] = bv;
-    const float* trow = tile + ((size_t)(im * PH + h) * PW + w0) * kDwCC + c4 * 4;
+    for (int j = 0; j < kDwTW; ++j) { acc[0][j] = bv; acc[1][j] = bv; }
+    const float* trow = tile + ((size_t)(im * PH + h0) * PW + w0) * kDwCC + lane;
 #pragma unroll
-    for (int r = 0; r < 5; ++r) {
-      float4 win[kDwTW + 4];
+    for (int ri = 0; ri < 6; ++ri) {
+      if (ri == 5 && h0 + 1 >= H) break;  // the sixth window row only feeds the second output row
+      float win[kDwTW + 4];
 #pragma unroll
-      for (int j = 0; j < kDwTW + 4; ++j)
-        win[j] = *reinterpret_cast<const float4*>(trow + ((size_t)r * PW + j) * kDwCC);
+      for (int j = 0; j < kDwTW + 4; ++j) win[j] = trow[((size_t)ri * PW + j) * kDwCC];
 #pragma unroll
-      for (int s = 0; s < 5; ++s) {
-        const float4 wv = *reinterpret_cast<const float4*>(wsm + (r * 5 + s) * kDwCC + c4 * 4);
+      for (int o = 0; o < 2; ++o) {
+        const int tr = ri - o;
+        if (tr < 0 || tr > 4) continue;
 #pragma unroll
-        for (int j = 0; j < kDwTW; ++j) {
-          acc[j].x = fmaf(win[j + s].x, wv.x, acc[j].x); acc[j].y = fmaf(win[j + s].y, wv.y, acc[j].y);
-          acc[j].z = fmaf(win[j + s].z, wv.z, acc[j].z); acc[j].w = fmaf(win[j + s].w, wv.w, acc[j].w);
-        }
+        for (int s = 0; s < 5; ++s)
+#pragma unroll
+          for (int j = 0; j < kDwTW; ++j) acc[o][j] = fmaf(win[j + s], wreg[tr * 5 + s], acc[o][j]);
       }
     }
-    float* yo = y + (((int64_t)(n0 + im) * H + h) * W + w0) * C + c0 + c4 * 4;
 #pragma unroll
-    for (int j = 0; j < kDwTW; ++j)
-      if (w0 + j < W) stg4(yo + (int64_t)j * C, acc[j]);
+    for (int o = 0; o < 2; ++o) {
+      if (h0 + o >= H) break;
+      float* yo = y + (((int64_t)(n0 + im) * H + h0 + o) * W + w0) * C + c0 + lane;
+#pragma unroll
+      for (int j = 0; j < kDwTW; ++j)
+        if (w0 + j < W) yo[(int64_t)j * C] = acc[o][j];
+    }
   }
 }
 
-// Backward-filter: dw[tap][c] = sum_pix a[pix + tap][c] * dy[pix][c], db[c] = sum dy.  Thread (pixel group pg of 32,
-// channel quad c4 of 8) keeps all 25 tap sums + the bias sum in registers and walks its pixels; the 32 pixel groups
-// are then combined by two warp shuffles and an 8-warp shared-memory sum, all in fixed order (deterministic).
+// Backward-filter: dw[tap][c] = sum_pix a[pix + tap][c] * dy[pix][c], db[c] = sum dy.  A thread is one channel (a
+// warp = the chunk's 32 channels at one image row): it keeps the dy row and one input row in registers and
+// accumulates all 25 taps + the bias sum (0.3 shared loads per FMA).  The 8 warps are then combined through
+// shared memory in warp order (deterministic).  WT = row width the registers are sized for (>= W).
 // partial[g][26][C]: taps 0..24, 25 = sum dy (bias gradient)
+template <int WT>
 __global__ void __launch_bounds__(kDwThreads, 2) dwconv5x5_bwd_filter_kernel(
     const float* __restrict__ x, const float* __restrict__ stat, int act, const float* __restrict__ dy, int N, int H,
     int W, int C, float* __restrict__ partial, int imgs, int PH, int PW) {
@@ -161,39 +168,35 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv5x5_bwd_filter_kernel(
     }
   }
   dw_stage<true>(tile, x, stat, act, n0, nimg, H, W, C, c0, PH, PW);  // ends with __syncthreads
-  float4 acc[26];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[26];
 #pragma unroll
-  for (int i = 0; i < 26; ++i) acc[i] = make_float4(0, 0, 0, 0);
-  for (int p = pg; p < npix; p += kDwThreads >> 3) {
-    const int im = p / HW, q = p - im * HW, h = q / W, w = q - h * W;
-    const float4 d = *reinterpret_cast<const float4*>(dtile + (size_t)p * kDwCC + c4 * 4);
-    const float* ar = tile + ((size_t)(im * PH + h) * PW + w) * kDwCC + c4 * 4;
+  for (int i = 0; i < 26; ++i) acc[i] = 0.f;
+  for (int it = warp; it < nimg * H; it += kDwThreads / 32) {
+    const int im = it / H, h = it - im * H;
+    float dyr[WT];
+    const float* dr = dtile + ((size_t)(im * H + h) * W) * kDwCC + lane;
 #pragma unroll
-    for (int r = 0; r < 5; ++r)
+    for (int j = 0; j < WT; ++j) {
+      dyr[j] = j < W ? dr[(size_t)j * kDwCC] : 0.f;
+      acc[25] += dyr[j];
+    }
 #pragma unroll
-      for (int s = 0; s < 5; ++s) {
-        const float4 a = *reinterpret_cast<const float4*>(ar + ((size_t)r * PW + s) * kDwCC);
-        float4& t = acc[r * 5 + s];
-        t.x = fmaf(a.x, d.x, t.x); t.y = fmaf(a.y, d.y, t.y); t.z = fmaf(a.z, d.z, t.z); t.w = fmaf(a.w, d.w, t.w);
-      }
-    acc[25].x += d.x; acc[25].y += d.y; acc[25].z += d.z; acc[25].w += d.w;
-  }
-  // pixel groups of one warp (lanes differing in bits 3,4), then the 8 warps through shared memory
+    for (int r = 0; r < 5; ++r) {
+      float xr[WT + 4];
+      const float* ar = tile + ((size_t)(im * PH + h + r) * PW) * kDwCC + lane;
 #pragma unroll
-  for (int i = 0; i < 26; ++i) {
+      for (int j = 0; j < WT + 4; ++j) xr[j] = j < W + 4 ? ar[(size_t)j * kDwCC] : 0.f;
 #pragma unroll
-    for (int o = 8; o < 32; o <<= 1) {
-      acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, o); acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, o);
-      acc[i].z += __shfl_xor_sync(0xffffffffu, acc[i].z, o); acc[i].w += __shfl_xor_sync(0xffffffffu, acc[i].w, o);
+      for (int s = 0; s < 5; ++s)
+#pragma unroll
+        for (int j = 0; j < WT; ++j) acc[r * 5 + s] = fmaf(xr[j + s], dyr[j], acc[r * 5 + s]);
     }
   }
   __syncthreads();  // every thread is done with dtile
   float* red = dtile;  // [8 warps][26][32]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane < 8) {
 #pragma unroll
-    for (int i = 0; i < 26; ++i) *reinterpret_cast<float4*>(red + ((size_t)warp * 26 + i) * kDwCC + lane * 4) = acc[i];
-  }
+  for (int i = 0; i < 26; ++i) red[((size_t)warp * 26 + i) * kDwCC + lane] = acc[i];
   __syncthreads();
   for (int i = threadIdx.x; i < 26 * kDwCC; i += kDwThreads) {
     float s = 0.f;
@@ -235,7 +238,7 @@ template <bool FLIP>
 static int dw_launch(const float* x, const float* stat, int act, int N, int H, int W, int C, const float* w,
                      const float* bias, float* y, cudaStream_t stream) {
   DwGeom g = dw_geom(N, H, W, C);
-  const size_t smem = (g.smem_tile + 25 * kDwCC) * sizeof(float);
+  const size_t smem = g.smem_tile * sizeof(float);
   static size_t configured[2] = {0, 0};
   if (smem > configured[FLIP]) {
     NVAE_CUDA_TRY(cudaFuncSetAttribute(dwconv5x5_kernel<FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -280,15 +283,24 @@ extern "C" int nvae_dwconv5x5_bwd_filter(const float* x, const float* stat, int 
   size_t dfloats = (size_t)g.imgs * H * W * kDwCC;
   if (dfloats < (size_t)(kDwThreads / 32) * 26 * kDwCC) dfloats = (size_t)(kDwThreads / 32) * 26 * kDwCC;  // cross-warp buffer
   const size_t smem = (g.smem_tile + dfloats) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    NVAE_CUDA_TRY(cudaFuncSetAttribute(dwconv5x5_bwd_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       200 * 1024));
-    configured = true;
-  }
   float* partial = reinterpret_cast<float*>(ws);
-  dwconv5x5_bwd_filter_kernel<<<dim3(g.nchunks, g.ngroups), kDwThreads, smem, stream>>>(x, stat, act, dy, N, H, W, C,
-                                                                                        partial, g.imgs, g.PH, g.PW);
+  const dim3 grid(g.nchunks, g.ngroups);
+#define NVAE_DW_FILTER(WT_)                                                                                           \
+  do {                                                                                                                \
+    static bool configured = false;                                                                                   \
+    if (!configured) {                                                                                                \
+      NVAE_CUDA_TRY(cudaFuncSetAttribute(dwconv5x5_bwd_filter_kernel<WT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         200 * 1024));                                                                \
+      configured = true;                                                                                              \
+    }                                                                                                                 \
+    dwconv5x5_bwd_filter_kernel<WT_><<<grid, kDwThreads, smem, stream>>>(x, stat, act, dy, N, H, W, C, partial, g.imgs, \
+                                                                         g.PH, g.PW);                                 \
+  } while (0)
+  if (W <= 4) NVAE_DW_FILTER(4);
+  else if (W <= 8) NVAE_DW_FILTER(8);
+  else if (W <= 16) NVAE_DW_FILTER(16);
+  else return NVAE_E_UNSUPPORTED;
+#undef NVAE_DW_FILTER
   NVAE_RETURN_IF_LAUNCH_FAILED();
   dwconv5x5_bwd_filter_reduce_kernel<<<(26 * C + 255) / 256, 256, 0, stream>>>(partial, g.ngroups, C, dw, dbias);
   NVAE_RETURN_IF_LAUNCH_FAILED();
