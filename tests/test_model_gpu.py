@@ -156,6 +156,32 @@ def test_default_config_step_against_live_oracle(lib_built, batch, steps, traini
         assert H.max_rel_err(npy(m.rt.variables[n].value), v) < TOL_ACT, n
 
 
+def test_cifar_shape_three_scales_against_live_oracle(lib_built):
+    """BASELINE configs[4]: 32x32x3 input, deeper hierarchy (three latent scales: 8x8, 4x4, 2x2).  The head keeps the
+    reference's single output channel (postprocess.py:29), so the logits broadcast over the 3 input channels in
+    the Bernoulli log-likelihood (README.md:25-27) -- parity with that behaviour, not a redesign."""
+    cfg = O.NVAEConfig(n_encoder_channels=8, n_decoder_channels=8, n_latent_per_group=8, n_groups_per_scale=(2, 3, 4),
+                       n_preprocess_cells=2, n_post_process_cells=2, image_channels=3, n_total_iterations=100)
+    batch, steps = 4, 20
+    params, trainable, bnl, s = O.build_params(cfg, seed=5, jitter=0.1)
+    params = {k: f32(v) for k, v in params.items()}
+    x = O.make_images(cfg, batch, seed=5).numpy()
+    assert x.shape == (batch, 32, 32, 3)
+    eps = [f32(e.numpy()) for e in O.make_eps(s, batch, seed=5)]
+    losses, grads, c, record = H.run_oracle_step(cfg, params, trainable, bnl, s, x, eps, steps, True)
+    m = _make_model(cfg, batch, True)
+    assert m.decoder.sampler.n_groups == 9
+    m.rt.load_named(params)
+    m.rt.inject_eps(eps)
+    m.steps = steps
+    out = m.train_step(x, apply_gradients=False)
+    assert abs(float(out["loss"].item()) - float(losses["loss"])) <= TOL_LOSS * abs(float(losses["loss"]))
+    assert H.max_rel_err(npy(out["reconstruction_loss"]), losses["reconstruction_loss"]) < TOL_LOSS
+    assert H.max_rel_err(npy(m.decoder.sampler.kl_all), losses["kl_all"]) < TOL_LOSS
+    worst = H.compare_grads(m.rt.named_grads(), grads, TOL_ACT)
+    assert worst[1] < TOL_ACT, worst
+
+
 def test_optimizer_update_and_second_step(lib_built):
     """apply_gradients: Adamax + CosineDecay on the flat arena == per-variable oracle updates; step 2 still agrees."""
     cfg = H.oracle_cfg()
