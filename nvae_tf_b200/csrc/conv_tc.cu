@@ -710,11 +710,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // g, g+KG, ... in order, four loads in flight -- and the group sums are combined in group order: a fixed tree,
 // so results are bit-repeatable.
 constexpr int kFixThreads = 256;
+// CTAs whose first segment completes a split tile (host-computed: the fix-up launches one block row per entry
+// instead of one per CTA, most of which would exit at once)
+struct FixList {
+  int n;
+  uint8_t cta[148];
+};
 constexpr int kFixMaxGroups = 8;
 template <bool WGRAD>
-__global__ void __launch_bounds__(kFixThreads) conv_tc_fixup_kernel(const TcParams p, int G, int rows) {
+__global__ void __launch_bounds__(kFixThreads) conv_tc_fixup_kernel(const TcParams p, int G, int rows,
+                                                                    const FixList fl) {
   __shared__ float4 red[kFixThreads];
-  const int c = blockIdx.x;
+  const int c = fl.cta[blockIdx.x];
   const long long u0 = cta_u0(p, c, G), u1 = cta_u0(p, c + 1, G);
   const int t = (int)(u0 / p.KU);
   if (u0 == (long long)t * p.KU) return;               // CTA c starts on a tile boundary
@@ -1048,9 +1055,19 @@ int launch(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t 
     // few split tiles -> fewer rows per block, so the fix-up still fills the machine and sums partials in parallel
     const long long T = (long long)pl.n_mtiles * pl.n_ntiles;
     const long long tiles = T < pl.G ? T : pl.G;
-    int rows = 32;
-    while (rows > 1 && tiles * (kBM / rows) < 2 * kNumSMs) rows >>= 1;
-    conv_tc_fixup_kernel<WGRAD><<<dim3(pl.G, kBM / rows), kFixThreads, 0, stream>>>(p, pl.G, rows);
+    (void)tiles;
+    FixList fl;
+    fl.n = 0;
+    for (int c = 1; c < pl.G; ++c) {  // same arithmetic as cta_u0 with whole_tiles == 0
+      const long long u0 = (long long)c * pl.U / pl.G, u1 = (long long)(c + 1) * pl.U / pl.G;
+      const long long t = u0 / pl.KU;
+      if (u0 != t * pl.KU && u1 >= (t + 1) * pl.KU) fl.cta[fl.n++] = (uint8_t)c;
+    }
+    if (fl.n > 0) {
+      int rows = 32;
+      while (rows > 1 && (long long)fl.n * (kBM / rows) < 2 * kNumSMs) rows >>= 1;
+      conv_tc_fixup_kernel<WGRAD><<<dim3(fl.n, kBM / rows), kFixThreads, 0, stream>>>(p, pl.G, rows, fl);
+    }
     NVAE_RETURN_IF_LAUNCH_FAILED();
   }
   return NVAE_OK;
