@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(kSnThreads) sn_scale_pack_kernel(float* __rest
                                                                    const int32_t* __restrict__ chunk_layer,
                                                                    const float* __restrict__ sigma, int power_iter,
                                                                    int pack_exact) {
-  __shared__ float tile[kSnRows][33];
+  constexpr int kTC = 64;  // columns per transposition tile
+  __shared__ float tile[kSnRows][kTC + 1];
   const int li = chunk_layer[blockIdx.x];
   const NvaeSnLayer L = layers[li];
   const int chunk = blockIdx.x - L.chunk0;
@@ -106,28 +107,55 @@ __global__ void __launch_bounds__(kSnThreads) sn_scale_pack_kernel(float* __rest
   const int r0 = chunk * kSnRows;
   const int nr = (L.rows - r0) < kSnRows ? (L.rows - r0) : kSnRows;
   const int K = L.taps * L.cin_pad;
-  for (int cb = 0; cb < L.cout; cb += 32) {
-    // load [nr][32] tile: threads map co fastest
-    for (int i = threadIdx.x; i < kSnRows * 32; i += kSnThreads) {
-      const int r = i >> 5, c = cb + (i & 31);
-      float v = 0.f;
-      if (r < nr && c < L.cout) {
-        const int64_t o = (int64_t)(r0 + r) * L.cout + c;
-        v = W[o] * inv_sigma;
-        if (power_iter) W[o] = v;
-        if (L.rnd_off >= 0) pack[L.rnd_off + o] = pack_exact ? v : round_tf32(v);
+  // Phase 1: the chunk's rows are one contiguous block of nr*cout floats -> streaming in-place scale (and the
+  // HWIO operand copy), 128-bit accesses, four independent loads in flight per thread.
+  if (power_iter || L.rnd_off >= 0) {
+    const int64_t base = (int64_t)r0 * L.cout, n = (int64_t)nr * L.cout;
+    float* wb = W + base;
+    float* pb = L.rnd_off >= 0 ? pack + L.rnd_off + base : nullptr;
+    if ((((uintptr_t)wb | (uintptr_t)pb) & 15u) == 0 && (n & 3) == 0) {
+      const int64_t n4 = n >> 2;
+      for (int64_t i0 = threadIdx.x; i0 < n4; i0 += 4 * kSnThreads) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t i = i0 + (int64_t)j * kSnThreads;
+          v[j] = i < n4 ? *reinterpret_cast<const float4*>(wb + 4 * i) : make_float4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t i = i0 + (int64_t)j * kSnThreads;
+          if (i >= n4) continue;
+          v[j].x *= inv_sigma; v[j].y *= inv_sigma; v[j].z *= inv_sigma; v[j].w *= inv_sigma;
+          if (power_iter) stg4(wb + 4 * i, v[j]);
+          if (pb != nullptr)
+            stg4(pb + 4 * i, pack_exact ? v[j] : make_float4(round_tf32(v[j].x), round_tf32(v[j].y), round_tf32(v[j].z),
+                                                                 round_tf32(v[j].w)));
+        }
       }
-      tile[r][i & 31] = v;
+    } else {
+      for (int64_t i = threadIdx.x; i < n; i += kSnThreads) {
+        const float v = wb[i] * inv_sigma;
+        if (power_iter) wb[i] = v;
+        if (pb != nullptr) pb[i] = pack_exact ? v : round_tf32(v);
+      }
+    }
+    __syncthreads();  // phase 2 re-reads the scaled block (same CTA, global memory)
+  }
+  if (L.tr_off < 0) return;
+  // Phase 2: transposed operand copy [cout][taps][cin_pad] through shared memory (reads co-fastest, writes ci-fastest)
+  for (int cb = 0; cb < L.cout; cb += kTC) {
+    for (int i = threadIdx.x; i < kSnRows * kTC; i += kSnThreads) {
+      const int r = i / kTC, cc = i - r * kTC, c = cb + cc;
+      tile[r][cc] = (r < nr && c < L.cout) ? W[(int64_t)(r0 + r) * L.cout + c] : 0.f;
     }
     __syncthreads();
-    if (L.tr_off >= 0) {
-      for (int i = threadIdx.x; i < kSnRows * 32; i += kSnThreads) {
-        const int r = i % kSnRows, c = cb + i / kSnRows;
-        if (r < nr && c < L.cout) {
-          const int row = r0 + r, tap = row / L.cin, ci = row - tap * L.cin;
-          const float v = tile[r][i / kSnRows];
-          pack[L.tr_off + (int64_t)c * K + (int64_t)tap * L.cin_pad + ci] = pack_exact ? v : round_tf32(v);
-        }
+    for (int i = threadIdx.x; i < kSnRows * kTC; i += kSnThreads) {
+      const int r = i % kSnRows, cc = i / kSnRows, c = cb + cc;
+      if (r < nr && c < L.cout) {
+        const int row = r0 + r, tap = row / L.cin, ci = row - tap * L.cin;
+        const float v = tile[r][cc];
+        pack[L.tr_off + (int64_t)c * K + (int64_t)tap * L.cin_pad + ci] = pack_exact ? v : round_tf32(v);
       }
     }
     __syncthreads();
