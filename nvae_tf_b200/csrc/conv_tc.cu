@@ -28,6 +28,8 @@
 // 128-bit stores) on a double-buffered TMEM accumulator, so the next tile's MMAs overlap the drain.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "conv_internal.h"
 
 using namespace nvae;
@@ -131,6 +133,47 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// cta_group::2 forms: ONE instruction, issued by the leader CTA of a 2-CTA cluster, drives both SMs' tensor cores --
+// D[256 x N]: each CTA's TMEM holds its 128 rows of A and of D, each CTA's shared memory holds N/2 rows of B.
+__device__ __forceinline__ void umma_tf32_ts_2cta(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all previously issued MMAs completed) on the barrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// arrive on the barrier at this shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank) : "memory");
+}
 // arrives on the mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -159,9 +202,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (layout << 61);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, M=128, N=n
-__host__ __device__ inline uint32_t umma_idesc_tf32(int n, int a_mn_major, int b_mn_major) {
+__host__ __device__ inline uint32_t umma_idesc_tf32(int n, int a_mn_major, int b_mn_major, int m = kBM) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 
@@ -206,7 +249,6 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
 }
 // TMEM columns. TF32: two accumulators of tmem_cols_for(BN).  3xTF32 (BN <= 192): all 512 columns -- accumulators
 // packed at [0, BN) and [BN, 2BN), and for forward/dgrad the A operand ring at 384: slot s = {hi 32 cols, lo 32 cols}.
-constexpr uint32_t kTmemAcol = 384;
 __device__ __forceinline__ uint32_t tmem_alloc_cols(int bn, int passes) {
   return passes == 3 ? 512u : 2u * tmem_cols_for(bn);
 }
@@ -227,6 +269,10 @@ struct TcParams {
   int N, H, W;
   int tw, th, tn, tiles_h;      // box extent; rows per box = tw*th*tn
   // tiles and the stream-K partition
+  int acc_bufs;                 // TMEM accumulators: 2 (a tile's epilogue overlaps the next tile's MMAs) or 1 (long K:
+                                // the columns go to a deeper A ring instead, so the converters run further ahead)
+  int pair;                     // launched as 2-CTA clusters (cta_group::2): tiles are 256 pixel rows, B is split
+  int n_mtiles;                 // 128-row M tiles of the problem (a pair's second tile may lie beyond it)
   int a_tmem;                   // 3xTF32: A (high and low parts) is staged in TMEM by the converters, only B lo in smem
   int BN, stages, lo_stages, passes;  // raw-tile ring, lo-tile ring (3xTF32 only); passes: 1 = TF32, 3 = 3xTF32
   int n_ntiles;                 // tile t = mt * n_ntiles + nt
@@ -311,7 +357,7 @@ __device__ __forceinline__ RowCtx row_ctx(const TcParams& p, int mt, int row) {
     const int per_img = p.tw * p.th;
     const int in = row / per_img, rem = row - in * per_img;
     const int ih = rem / p.tw, iw = rem - ih * p.tw;
-    r.ok = row < per_img * p.tn && (n0 + in) < p.N && (h0 + ih) < p.H;
+    r.ok = mt < p.n_mtiles && row < per_img * p.tn && (n0 + in) < p.N && (h0 + ih) < p.H;
     r.base = ((int64_t)(n0 + in) * p.oH + (h0 + ih) * p.os + p.ooh) * p.oW + iw * p.os + p.oow;
   } else {
     const int nch = p.nchunk1 + p.nchunk2;
@@ -368,7 +414,11 @@ __device__ __forceinline__ float4 tf32_lo4(const float4& v) {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <bool WGRAD>
+// PAIR: forward / dgrad in 3xTF32 as 2-CTA clusters (cta_group::2).  The pair owns a 256-pixel x BN tile: each CTA
+// stages its own 128 pixel rows of A (-> its TMEM) and HALF of the B tile (BN/2 weight rows) in its shared memory, the
+// leader issues the MMAs for both SMs.  Per SM this halves the B bytes moved by TMA, split by the converters and
+// read by the MMAs -- the shared-memory port, not the tensor pipe, is what bounds the single-CTA kernel.
+template <bool WGRAD, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw);
@@ -380,7 +430,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t lo_base = stage_base + (uint32_t)p.stages * raw_bytes;
   const uint32_t lo_bytes = p.a_tmem ? p.b_bytes : raw_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = gridDim.x, cta = blockIdx.x;
+  // PAIR: the work unit space is over 256-row pair tiles and is cut over gridDim.x / 2 pairs
+  const int G = PAIR ? gridDim.x >> 1 : gridDim.x, cta = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   const long long u_begin = cta_u0(p, cta, G), u_end = cta_u0(p, cta + 1, G);
   const int nch = p.nchunk1 + p.nchunk2;
   const SegOrder so = seg_order(u_begin, u_end, p.KU, WGRAD);
@@ -392,21 +444,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(smem_u32(&ctl->empty[i]), 1);
     }
     for (int i = 0; i < p.lo_stages; ++i) {
-      mbar_init(smem_u32(&ctl->conv[i]), kConvThreads / 32);
+      mbar_init(smem_u32(&ctl->conv[i]), (PAIR ? 2 : 1) * (kConvThreads / 32));  // PAIR: both CTAs' converters
       mbar_init(smem_u32(&ctl->lo_empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&ctl->acc_full[i]), 1);
-      mbar_init(smem_u32(&ctl->acc_empty[i]), kEpiThreads / 32);
+      mbar_init(smem_u32(&ctl->acc_empty[i]), (PAIR ? 2 : 1) * (kEpiThreads / 32));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tma_prefetch_desc(&maps.m[0]);
     tma_prefetch_desc(&maps.m[2]);
   }
-  if (warp == 1) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_alloc_cols(p.BN, p.passes));
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2cta(smem_u32(&ctl->tmem_base), tmem_alloc_cols(p.BN, p.passes));
+    else tmem_alloc(smem_u32(&ctl->tmem_base), tmem_alloc_cols(p.BN, p.passes));
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem = ctl->tmem_base;
   if (threadIdx.x == 0) TC_STAMP(1);
@@ -419,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (long long u = so.lo[ph], u_end = so.hi[ph]; u < u_end;) {
         const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
         const int kb = (int)min((long long)p.KU, ka + (u_end - u));
-        const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
+        const int mt = PAIR ? 2 * (t / p.n_ntiles) + (int)crank : t / p.n_ntiles, nt = t - (t / p.n_ntiles) * p.n_ntiles;
         if (!WGRAD) {
           int n0, h0;
           if (p.tn > 1) { n0 = mt * p.tn; h0 = 0; }
@@ -447,7 +503,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               tma_load_4d(sa, &maps.m[1], full, (c - p.nchunk1) * kChunk, aw, ah, n0);
               kk = p.k2_base + (c - p.nchunk1) * kChunk;
             }
-            tma_load_2d(sa + p.a_bytes, &maps.m[2], full, wt * p.bk_tap + kk, wt * p.br_tap + nt * p.BN);
+            // PAIR: this CTA's half of the B tile (p.b_bytes covers BN/2 rows)
+            tma_load_2d(sa + p.a_bytes, &maps.m[2], full, wt * p.bk_tap + kk,
+                        wt * p.br_tap + nt * p.BN + (PAIR ? (int)crank * (p.BN >> 1) : 0));
             if (++c == nch) { c = 0; ++tap; }
           }
         } else {
@@ -493,10 +551,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer (PAIR: the leader CTA only) ----------------
+    if (lane == 0 && (!PAIR || crank == 0)) {
       const uint32_t idesc = WGRAD ? umma_idesc_tf32(p.BN, 1, 1) : umma_idesc_tf32(p.BN, 0, 0);
-      const uint32_t idesc_ts = umma_idesc_tf32(p.BN, 0, WGRAD ? 1 : 0);  // A from TMEM is K-major by construction
+      // A from TMEM is K-major by construction; a pair MMA spans 256 rows
+      const uint32_t idesc_ts = umma_idesc_tf32(p.BN, 0, WGRAD ? 1 : 0, PAIR ? 2 * kBM : kBM);
       const uint32_t box_bytes = (uint32_t)p.KP * 128u;
       const int ksteps = WGRAD ? p.KP / 8 : 4;
       const uint64_t kadv = WGRAD ? 64u : 2u;  // descriptor start-address step per K=8: 8 pixel rows / 32 bytes
@@ -505,14 +564,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (long long u = so.lo[ph], u_end = so.hi[ph]; u < u_end; ++seg) {
         const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
         const int kb = (int)min((long long)p.KU, ka + (u_end - u));
-        const uint32_t acc = tmem + (uint32_t)(seg & 1) * tmem_acc_stride(p.BN, p.passes);
-        mbar_wait(smem_u32(&ctl->acc_empty[seg & 1]), (((uint32_t)seg >> 1) & 1u) ^ 1u);
+        const int ab = seg % p.acc_bufs;
+        const uint32_t acc = tmem + (uint32_t)ab * tmem_acc_stride(p.BN, p.passes);
+        mbar_wait(smem_u32(&ctl->acc_empty[ab]), (((uint32_t)(seg / p.acc_bufs)) & 1u) ^ 1u);
         tc_fence_after();
         for (int k = ka; k < kb; ++k, ++it) {
           const int st = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          mbar_wait(smem_u32(&ctl->full[st]), ph);
-          tc_fence_after();
+          if (!PAIR) {  // (PAIR: the converters of both CTAs vouch for the tiles through conv[])
+            mbar_wait(smem_u32(&ctl->full[st]), ph);
+            tc_fence_after();
+          }
           if (it == 0) TC_STAMP(2);
           const uint32_t sa = stage_base + (uint32_t)st * stage_bytes;
           uint64_t da, db;
@@ -545,17 +607,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             } else {
               // A (high and low parts) comes from TMEM: only B crosses the shared-memory port, three times
               const uint64_t lb = WGRAD ? umma_desc_sw128(sl, box_bytes, 512, 1) : umma_desc_sw128(sl, 16, 1024);
-              const uint32_t a_hi = tmem + kTmemAcol + (uint32_t)ls * 64u, a_lo = a_hi + 32u;
-              for (int j = 0; j < 4; ++j)
-                umma_tf32_ts(acc, a_hi + 8u * j, db + kadv * j, idesc_ts, (k > ka || j > 0) ? 1u : 0u);
-              for (int j = 0; j < 4; ++j) umma_tf32_ts(acc, a_hi + 8u * j, lb + kadv * j, idesc_ts, 1u);
-              for (int j = 0; j < 4; ++j) umma_tf32_ts(acc, a_lo + 8u * j, db + kadv * j, idesc_ts, 1u);
+              const uint32_t a_hi = tmem + (uint32_t)(p.acc_bufs * p.BN) + (uint32_t)ls * 64u, a_lo = a_hi + 32u;
+              if (PAIR) {
+                for (int j = 0; j < 4; ++j)
+                  umma_tf32_ts_2cta(acc, a_hi + 8u * j, db + kadv * j, idesc_ts, (k > ka || j > 0) ? 1u : 0u);
+                for (int j = 0; j < 4; ++j) umma_tf32_ts_2cta(acc, a_hi + 8u * j, lb + kadv * j, idesc_ts, 1u);
+                for (int j = 0; j < 4; ++j) umma_tf32_ts_2cta(acc, a_lo + 8u * j, db + kadv * j, idesc_ts, 1u);
+              } else {
+                for (int j = 0; j < 4; ++j)
+                  umma_tf32_ts(acc, a_hi + 8u * j, db + kadv * j, idesc_ts, (k > ka || j > 0) ? 1u : 0u);
+                for (int j = 0; j < 4; ++j) umma_tf32_ts(acc, a_hi + 8u * j, lb + kadv * j, idesc_ts, 1u);
+                for (int j = 0; j < 4; ++j) umma_tf32_ts(acc, a_lo + 8u * j, db + kadv * j, idesc_ts, 1u);
+              }
             }
-            umma_commit(smem_u32(&ctl->lo_empty[ls]));
+            if (PAIR) umma_commit_2cta(smem_u32(&ctl->lo_empty[ls]));
+            else umma_commit(smem_u32(&ctl->lo_empty[ls]));
           }
-          umma_commit(smem_u32(&ctl->empty[st]));
+          if (PAIR) umma_commit_2cta(smem_u32(&ctl->empty[st]));
+          else umma_commit(smem_u32(&ctl->empty[st]));
         }
-        umma_commit(smem_u32(&ctl->acc_full[seg & 1]));
+        if (PAIR) umma_commit_2cta(smem_u32(&ctl->acc_full[ab]));
+        else umma_commit(smem_u32(&ctl->acc_full[ab]));
         TC_STAMP(3);
         u += kb - ka;
       }
@@ -612,7 +684,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               lw[kk] = __float_as_uint(tf32_lo(v));
             }
           }
-          const uint32_t ta = tmem + kTmemAcol + (uint32_t)ls * 64u + (uint32_t)half * 16u + ((uint32_t)((warp & 3) * 32) << 16);
+          const uint32_t ta = tmem + (uint32_t)(p.acc_bufs * p.BN) + (uint32_t)ls * 64u + (uint32_t)half * 16u +
+                              ((uint32_t)((warp & 3) * 32) << 16);
           tmem_st16(ta, hi);
           tmem_st16(ta + 32u, lw);
           src = reinterpret_cast<const float4*>(raw + p.a_bytes);
@@ -636,7 +709,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&ctl->conv[ls]));
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(smem_u32(&ctl->conv[ls]), 0);  // the leader's barrier counts both CTAs
+          else mbar_arrive(smem_u32(&ctl->conv[ls]));
+        }
         if (it == 8 && ct == 0) TC_STAMP(12);
         if (it == 9 && ct == 0) TC_STAMP(13);
       }
@@ -652,16 +728,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (long long u = so.lo[ph], u_end = so.hi[ph]; u < u_end; ++seg) {
       const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
       const int kb = (int)min((long long)p.KU, ka + (u_end - u));
-      const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
+      const int mt = PAIR ? 2 * (t / p.n_ntiles) + (int)crank : t / p.n_ntiles, nt = t - (t / p.n_ntiles) * p.n_ntiles;
       const bool full_tile = ka == 0 && kb == p.KU;
       {
         const RowCtx rc = row_ctx<WGRAD>(p, mt, row);
         epi->rowbase[row] = (rc.ok || !full_tile) ? rc.base : -1;
       }
       // slot 0: continues a tile begun by an earlier CTA; slot 1: begins a tile a later CTA finishes
-      float* pdst = p.part + (((int64_t)cta * 2 + (ka > 0 ? 0 : 1)) * kBM + lg * 32) * p.BN;
-      const uint32_t acc = tmem + (uint32_t)(seg & 1) * tmem_acc_stride(p.BN, p.passes) + ((uint32_t)(lg * 32) << 16);
-      mbar_wait(smem_u32(&ctl->acc_full[seg & 1]), ((uint32_t)seg >> 1) & 1u);
+      // (PAIR: [pair][slot][rank][128][BN])
+      float* pdst = p.part + ((((int64_t)cta * 2 + (ka > 0 ? 0 : 1)) * (PAIR ? 2 : 1) + (PAIR ? crank : 0)) * kBM + lg * 32) * p.BN;
+      const int ab = seg % p.acc_bufs;
+      const uint32_t acc = tmem + (uint32_t)ab * tmem_acc_stride(p.BN, p.passes) + ((uint32_t)(lg * 32) << 16);
+      mbar_wait(smem_u32(&ctl->acc_full[ab]), ((uint32_t)(seg / p.acc_bufs)) & 1u);
       tc_fence_after();
       if (threadIdx.x == kThreads - 1) TC_STAMP(4);
       for (int j = 0; j < p.BN; j += 32) {
@@ -690,16 +768,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty[seg & 1]));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(smem_u32(&ctl->acc_empty[ab]), 0);
+        else mbar_arrive(smem_u32(&ctl->acc_empty[ab]));
+      }
       if (threadIdx.x == kThreads - 1) TC_STAMP(5);
       u += kb - ka;
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // neither CTA may leave (or free TMEM) while the pair's MMAs / arrivals can touch it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, tmem_alloc_cols(p.BN, p.passes));
+    if (PAIR) tmem_dealloc_2cta(tmem, tmem_alloc_cols(p.BN, p.passes));
+    else tmem_dealloc(tmem, tmem_alloc_cols(p.BN, p.passes));
     if (lane == 0) TC_STAMP(6);
   }
 }
@@ -727,12 +810,17 @@ __global__ void __launch_bounds__(kFixThreads) conv_tc_fixup_kernel(const TcPara
   if (u0 == (long long)t * p.KU) return;               // CTA c starts on a tile boundary
   if (u1 < (long long)(t + 1) * p.KU) return;          // ... or does not finish the tile
   const int cf = first_cta_of(p, t, G);
-  const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
+  // pair launches: c, cf index PAIRS; blockIdx.z picks the CTA of the pair (its 128-row half of the pair tile)
+  const int rk = p.pair ? (int)blockIdx.z : 0, nrk = p.pair ? 2 : 1;
+  const int mt = p.pair ? 2 * (t / p.n_ntiles) + rk : t / p.n_ntiles, nt = t - (t / p.n_ntiles) * p.n_ntiles;
+  if (mt >= p.n_mtiles) return;
   const int bn4 = p.BN / 4, total = rows * bn4, nparts = c - cf + 1;
   const int64_t slot = (int64_t)kBM * p.BN;
   const int64_t blk = (int64_t)blockIdx.y * rows * p.BN;
   // partial j of the tile: j = 0 -> CTA cf's slot 1 (it began the tile), j >= 1 -> CTA cf+j's slot 0
-  auto part_ptr = [&](int j) { return p.part + ((int64_t)(cf + j) * 2 + (j == 0 ? 1 : 0)) * slot + blk; };
+  auto part_ptr = [&](int j) {
+    return p.part + (((int64_t)(cf + j) * 2 + (j == 0 ? 1 : 0)) * nrk + rk) * slot + blk;
+  };
   int KG = kFixThreads / total;
   KG = KG < 1 ? 1 : (KG > kFixMaxGroups ? kFixMaxGroups : KG);
   if (KG > nparts) KG = nparts;
@@ -938,7 +1026,7 @@ bool common_ok(const NvaeConvDesc* d, int which) {
 // Launch plan shared by the three directions: tiles, stages, stream-K grid, partial-buffer size.
 struct Plan {
   PixTile t;
-  int BN, stages, lo_stages, a_tmem, n_mtiles, n_ntiles, KU, G, njobs;
+  int BN, stages, lo_stages, a_tmem, acc_bufs, pair, n_mtiles, n_ntiles, KU, G, njobs;
   uint32_t a_bytes, b_bytes;
   long long U;
   int whole_tiles;
@@ -952,6 +1040,27 @@ struct Plan {
 // 18-72 tiles, K up to 2304).  Times in microseconds, calibrated on B200 (one 32-deep K stage ~ 0.95 us in
 // 3xTF32, 0.35 us in TF32; fix-up ~ 5 us + partial traffic at ~3 TB/s).
 bool finish_plan(Plan* pl, int passes, bool wgrad) {
+  // pair launches: the schedulable tiles are 256-row pair tiles and the workers are the 74 CTA pairs
+  const int workers = pl->pair ? kNumSMs / 2 : kNumSMs;
+  const long long T = (long long)(pl->pair ? (pl->n_mtiles + 1) / 2 : pl->n_mtiles) * pl->n_ntiles;
+  pl->U = T * pl->KU;
+  const double t_unit = passes == 3 ? 0.95 : 0.35;
+  const double slot_us = (double)kBM * pl->BN * 4 * 2 / 3.0e6;  // one partial written + read back
+  pl->whole_tiles = 1;
+  pl->G = (int)(T < workers ? T : workers);
+  double best = (double)ceil_div(T, pl->G) * pl->KU * t_unit;
+  if (T < workers) {
+    for (int S = 2; S * T <= workers && 2 * S <= pl->KU; ++S) {  // S workers per tile, >= 2 stages each
+      const double t = (double)ceil_div(pl->KU, S) * t_unit + 5.0 + (double)S * T * slot_us;
+      if (t < best) { best = t; pl->whole_tiles = 0; pl->G = (int)(S * T); }
+    }
+  }
+  if (pl->U >= 2 * workers) {  // equal unit ranges over all workers (up to two partials each)
+    const double sk = (double)ceil_div(pl->U, workers) * t_unit + 5.0 + 2.0 * workers * slot_us;
+    if (sk < 0.95 * best) { best = sk; pl->whole_tiles = 0; pl->G = workers; }
+  }
+  pl->split = !pl->whole_tiles;
+  // ---- shared-memory rings and the TMEM split (needs the partition: units per worker) ----
   const size_t raw = (size_t)pl->a_bytes + pl->b_bytes;
   const size_t budget = (size_t)kSmemBudget - 2048;
   size_t lo_slot = 0;
@@ -959,36 +1068,38 @@ bool finish_plan(Plan* pl, int passes, bool wgrad) {
     pl->a_tmem = (!wgrad || pl->a_bytes == 4u * 32u * 128u) ? 1 : 0;  // wgrad: 32 pixels per stage fit the TMEM A ring
     lo_slot = pl->a_tmem ? pl->b_bytes : raw;
     pl->lo_stages = 2;
-    if (budget < 2 * lo_slot + 2 * raw) return false;
-    pl->stages = (int)((budget - 2 * lo_slot) / raw);
+    pl->acc_bufs = 2;
+    // pair launches with a long K loop: the cross-SM handshakes need the converters further ahead of the MMAs ->
+    // one accumulator, and its TMEM columns deepen the A ring (BN + 4 * 64 <= 512)
+    if (pl->pair && pl->a_tmem && pl->KU >= 32 && pl->U / pl->G >= 32 && pl->BN + 4 * 64 <= 512 &&
+        budget >= 4 * lo_slot + 3 * raw) {
+      pl->acc_bufs = 1;
+      pl->lo_stages = 4;
+    }
+    if (budget < pl->lo_stages * lo_slot + 2 * raw) return false;
+    pl->stages = (int)((budget - pl->lo_stages * lo_slot) / raw);
   } else {
     if (budget < 2 * raw) return false;
     pl->lo_stages = 0;
+    pl->acc_bufs = 2;
     pl->a_tmem = 0;
     pl->stages = (int)(budget / raw);
   }
   if (pl->stages > kMaxStages) pl->stages = kMaxStages;
   pl->smem = sizeof(SmemCtl) + 1024 + (size_t)pl->stages * raw + (size_t)pl->lo_stages * lo_slot + sizeof(EpiSmem);
-  const long long T = (long long)pl->n_mtiles * pl->n_ntiles;
-  pl->U = T * pl->KU;
-  const double t_unit = passes == 3 ? 0.95 : 0.35;
-  const double slot_us = (double)kBM * pl->BN * 4 * 2 / 3.0e6;  // one partial written + read back
-  pl->whole_tiles = 1;
-  pl->G = (int)(T < kNumSMs ? T : kNumSMs);
-  double best = (double)ceil_div(T, pl->G) * pl->KU * t_unit;
-  if (T < kNumSMs) {
-    for (int S = 2; S * T <= kNumSMs && 2 * S <= pl->KU; ++S) {  // S CTAs per tile, >= 2 stages each
-      const double t = (double)ceil_div(pl->KU, S) * t_unit + 5.0 + (double)S * T * slot_us;
-      if (t < best) { best = t; pl->whole_tiles = 0; pl->G = (int)(S * T); }
-    }
-  }
-  if (pl->U >= 2 * kNumSMs) {  // equal unit ranges over all SMs (up to two partials per CTA)
-    const double sk = (double)ceil_div(pl->U, kNumSMs) * t_unit + 5.0 + 2.0 * kNumSMs * slot_us;
-    if (sk < 0.95 * best) { best = sk; pl->whole_tiles = 0; pl->G = kNumSMs; }
-  }
-  pl->split = !pl->whole_tiles;
-  pl->part_bytes = pl->split ? al256((size_t)pl->G * 2 * kBM * pl->BN * sizeof(float)) : 0;
+  pl->part_bytes = pl->split ? al256((size_t)pl->G * 2 * (pl->pair ? 2 : 1) * kBM * pl->BN * sizeof(float)) : 0;
   return true;
+}
+
+// Measured on B200 (5x5 384->384, batch 144): pairs 1.43 ms vs 1.10 ms for independent CTAs -- each SM's shared memory
+// still serves its half of B to BOTH tensor cores, so the MMA-side port traffic does not drop, and the cross-SM
+// handshakes lengthen the converter -> MMA chain.  Kept as an opt-in experiment (NVAE_TC_PAIR=1), off by default.
+bool pair_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("NVAE_TC_PAIR");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
 }
 
 // which: 0 forward, 1 dgrad; ntaps: K-loop taps (a stride-2 dgrad launch covers one output parity class)
@@ -997,19 +1108,22 @@ bool plan_gemm(const NvaeConvDesc* d, int which, int ntaps, Plan* pl) {
   const int passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
   const int Ct = d->Cin + d->Cin2;
   const int n_total = which == 0 ? d->Cout : Ct;
-  pl->BN = pick_bn(n_total, 16, passes == 3 ? 192 : 256);
   pl->n_mtiles = pl->t.n_tiles;
+  // 3xTF32 forward / dgrad run as 2-CTA pairs (N tile a multiple of 32: cta_group::2 MMA granularity)
+  pl->pair = passes == 3 && pl->n_mtiles >= 2 && pair_enabled();
+  pl->BN = pick_bn(n_total, pl->pair ? 32 : 16, passes == 3 ? 192 : 256);
   pl->n_ntiles = (int)ceil_div(n_total, pl->BN);
   const int nch = which == 0 ? (int)(ceil_div(d->Cin, kChunk) + ceil_div(d->Cin2, kChunk)) : (int)ceil_div(d->Cout, kChunk);
   pl->KU = ntaps * nch;
   pl->a_bytes = kBM * 128;
-  pl->b_bytes = (uint32_t)pl->BN * 128;
+  pl->b_bytes = (uint32_t)(pl->pair ? pl->BN / 2 : pl->BN) * 128;  // pair: each CTA stages half of the B tile
   pl->njobs = 0;
   return finish_plan(pl, passes, false);
 }
 
 bool plan_wgrad(const NvaeConvDesc* d, Plan* pl) {
   if (!common_ok(d, 2)) return false;
+  pl->pair = 0;
   const int passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
   if (!pick_pix_tile(d->N, d->Ho, d->Wo, 32, 8, &pl->t) && !pick_pix_tile(d->N, d->Ho, d->Wo, 64, 8, &pl->t) &&
       !pick_pix_tile(d->N, d->Ho, d->Wo, 128, 8, &pl->t))
@@ -1034,28 +1148,48 @@ void fill_common(TcParams* p, const NvaeConvDesc* d, const Plan& pl, float* part
   p->oH = d->Ho; p->oW = d->Wo; p->os = 1; p->ooh = 0; p->oow = 0;
   p->a5d = 0; p->par_c = d->Cin;
   p->tw = pl.t.tw; p->th = pl.t.th; p->tn = pl.t.tn; p->tiles_h = pl.t.tiles_h;
-  p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
+  p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->acc_bufs = pl.acc_bufs; p->pair = pl.pair; p->n_mtiles = pl.n_mtiles; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
   p->n_ntiles = pl.n_ntiles; p->KU = pl.KU; p->U = pl.U;
-  p->T = pl.n_mtiles * pl.n_ntiles; p->whole_tiles = pl.whole_tiles;
+  p->T = (pl.pair ? (pl.n_mtiles + 1) / 2 : pl.n_mtiles) * pl.n_ntiles; p->whole_tiles = pl.whole_tiles;
   p->a_bytes = pl.a_bytes; p->b_bytes = pl.b_bytes;
   p->part = part;
 }
 
-template <bool WGRAD>
-int launch(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t stream) {
+template <bool WGRAD, bool PAIR>
+int launch_main(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<WGRAD, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  conv_tc_kernel<WGRAD><<<pl.G, kThreads, pl.smem, stream>>>(maps, p);
-  NVAE_RETURN_IF_LAUNCH_FAILED();
+  if (!PAIR) {
+    conv_tc_kernel<WGRAD, PAIR><<<pl.G, kThreads, pl.smem, stream>>>(maps, p);
+    NVAE_RETURN_IF_LAUNCH_FAILED();
+    return NVAE_OK;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pl.G);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<WGRAD, PAIR>, maps, p);
+  ++nvae_launch_counter;
+  return e == cudaSuccess ? NVAE_OK : (int)e;
+}
+
+template <bool WGRAD>
+int launch(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t stream) {
+  int rc = (!WGRAD && pl.pair) ? launch_main<false, true>(maps, p, pl, stream) : launch_main<WGRAD, false>(maps, p, pl, stream);
+  if (rc) return rc;
   if (pl.split) {
-    // few split tiles -> fewer rows per block, so the fix-up still fills the machine and sums partials in parallel
-    const long long T = (long long)pl.n_mtiles * pl.n_ntiles;
-    const long long tiles = T < pl.G ? T : pl.G;
-    (void)tiles;
     FixList fl;
     fl.n = 0;
     for (int c = 1; c < pl.G; ++c) {  // same arithmetic as cta_u0 with whole_tiles == 0
@@ -1064,11 +1198,13 @@ int launch(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t 
       if (u0 != t * pl.KU && u1 >= (t + 1) * pl.KU) fl.cta[fl.n++] = (uint8_t)c;
     }
     if (fl.n > 0) {
+      // few split tiles -> fewer rows per block, so the fix-up still fills the machine
+      const int nrk = pl.pair ? 2 : 1;
       int rows = 32;
-      while (rows > 1 && (long long)fl.n * (kBM / rows) < 2 * kNumSMs) rows >>= 1;
-      conv_tc_fixup_kernel<WGRAD><<<dim3(fl.n, kBM / rows), kFixThreads, 0, stream>>>(p, pl.G, rows, fl);
+      while (rows > 1 && (long long)fl.n * nrk * (kBM / rows) < 2 * kNumSMs) rows >>= 1;
+      conv_tc_fixup_kernel<WGRAD><<<dim3(fl.n, kBM / rows, nrk), kFixThreads, 0, stream>>>(p, pl.G, rows, fl);
+      NVAE_RETURN_IF_LAUNCH_FAILED();
     }
-    NVAE_RETURN_IF_LAUNCH_FAILED();
   }
   return NVAE_OK;
 }
@@ -1142,7 +1278,7 @@ int nvae_conv2d_fwd_tc(const NvaeConvDesc* d, const float* x, const float* x2, c
   if (d->Cin2 > 0) rc = make_map_nhwc(&maps.m[1], x2, d->N, d->H, d->W, d->Cin2, d->Cin2, pl.t.tw, pl.t.th, pl.t.tn);
   else maps.m[1] = maps.m[0];
   if (rc) return rc;
-  rc = make_map_2d(&maps.m[2], w_tr, d->Cout, (int64_t)taps * Ct, pl.BN);
+  rc = make_map_2d(&maps.m[2], w_tr, d->Cout, (int64_t)taps * Ct, pl.pair ? pl.BN / 2 : pl.BN);
   if (rc) return rc;
   return launch<false>(maps, p, pl, stream);
 }
@@ -1188,7 +1324,7 @@ int nvae_conv2d_dgrad_tc(const NvaeConvDesc* d, const float* dy, const float* w_
     int rc = make_map_nhwc(&maps.m[0], dy + d->y_off, d->N, d->Ho, d->Wo, d->Cout, ld, pl.t.tw, pl.t.th, pl.t.tn);
     if (rc) return rc;
     maps.m[1] = maps.m[0];
-    rc = make_map_2d(&maps.m[2], w_rnd, (int64_t)taps * Ct, d->Cout, pl.BN);
+    rc = make_map_2d(&maps.m[2], w_rnd, (int64_t)taps * Ct, d->Cout, pl.pair ? pl.BN / 2 : pl.BN);
     if (rc) return rc;
     rc = launch<false>(maps, p, pl, stream);
     if (rc) return rc;
