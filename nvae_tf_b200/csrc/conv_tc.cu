@@ -218,11 +218,17 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 #define TC_STAMP(i) g_tc_timing[blockIdx.x * 16 + (i)] = gtime()
+__device__ long long g_tc_cyc[8 * 16];
+#define TC_CYC(it, j) do { if (blockIdx.x == 0 && (it) >= 8 && (it) < 16) g_tc_cyc[((it) - 8) * 16 + (j)] = clock64(); } while (0)
+extern "C" __attribute__((visibility("default"))) int nvae_debug_tc_cycles(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_tc_cyc, sizeof(g_tc_cyc));
+}
 extern "C" __attribute__((visibility("default"))) int nvae_debug_tc_timing(unsigned long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_tc_timing, sizeof(g_tc_timing));
 }
 #else
 #define TC_STAMP(i)
+#define TC_CYC(it, j)
 #endif
 
 struct SmemCtl {
@@ -444,7 +450,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(smem_u32(&ctl->empty[i]), 1);
     }
     for (int i = 0; i < p.lo_stages; ++i) {
-      mbar_init(smem_u32(&ctl->conv[i]), (PAIR ? 2 : 1) * (kConvThreads / 32));  // PAIR: both CTAs' converters
+      // a_tmem: one 4-warp converter group per stage (PAIR: of both CTAs); else all 8 converter warps
+      mbar_init(smem_u32(&ctl->conv[i]), (PAIR ? 2 : 1) * (p.a_tmem ? kConvThreads / 64 : kConvThreads / 32));
       mbar_init(smem_u32(&ctl->lo_empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -559,6 +566,75 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t box_bytes = (uint32_t)p.KP * 128u;
       const int ksteps = WGRAD ? p.KP / 8 : 4;
       const uint64_t kadv = WGRAD ? 64u : 2u;  // descriptor start-address step per K=8: 8 pixel rows / 32 bytes
+      if (p.a_tmem) {
+        // 3xTF32 fast path.  This ONE thread paces the tensor pipe (a tcgen05.mma costs it ~70 cycles to issue), so
+        // everything else in its loop is kept off the critical path: ring indices, barrier addresses and operand
+        // descriptors advance incrementally (no divisions), and the 12 MMAs of a stage are issued back to back.
+        constexpr uint64_t kAdv = WGRAD ? 64u : 2u;
+        const uint64_t b_desc0 = WGRAD ? umma_desc_sw128(stage_base + p.a_bytes, box_bytes, 512, 1)
+                                       : umma_desc_sw128(stage_base + p.a_bytes, 16, 1024);
+        const uint64_t lb_desc0 = WGRAD ? umma_desc_sw128(lo_base, box_bytes, 512, 1) : umma_desc_sw128(lo_base, 16, 1024);
+        const uint64_t st_step = (uint64_t)(stage_bytes >> 4), lo_step = (uint64_t)(lo_bytes >> 4);
+        const uint32_t a_base = tmem + (uint32_t)(p.acc_bufs * p.BN);
+        const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
+        const uint32_t conv0 = smem_u32(&ctl->conv[0]), loe0 = smem_u32(&ctl->lo_empty[0]);
+        int st = 0, ls = 0, seg = 0, it = 0;
+        uint32_t ph = 0, lph = 0, a_hi = a_base;
+        uint64_t db = b_desc0, lb = lb_desc0;
+        (void)it;
+        for (int sp = 0; sp < so.n; ++sp)
+        for (long long u = so.lo[sp], u_end = so.hi[sp]; u < u_end; ++seg) {
+          const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
+          const int kb = (int)min((long long)p.KU, ka + (u_end - u));
+          const int ab = seg % p.acc_bufs;
+          const uint32_t acc = tmem + (uint32_t)ab * tmem_acc_stride(p.BN, p.passes);
+          mbar_wait(smem_u32(&ctl->acc_empty[ab]), (((uint32_t)(seg / p.acc_bufs)) & 1u) ^ 1u);
+          tc_fence_after();
+          uint32_t accum = 0;
+          for (int k = ka; k < kb; ++k, ++it) {
+            TC_CYC(it, 13);
+            if (!PAIR) mbar_wait(full0 + 8u * st, ph);  // (PAIR: both CTAs' converters vouch for the tiles)
+            TC_CYC(it, 0);
+            mbar_wait(conv0 + 8u * ls, lph);
+            tc_fence_after();
+            TC_CYC(it, 1);
+            if (it == 0) TC_STAMP(2);
+            const uint32_t a_lo = a_hi + 32u;
+            if (PAIR) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_tf32_ts_2cta(acc, a_hi + 8u * j, db + kAdv * j, idesc_ts, accum | (j > 0));
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_tf32_ts_2cta(acc, a_hi + 8u * j, lb + kAdv * j, idesc_ts, 1u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_tf32_ts_2cta(acc, a_lo + 8u * j, db + kAdv * j, idesc_ts, 1u);
+              umma_commit_2cta(loe0 + 8u * ls);
+              umma_commit_2cta(empty0 + 8u * st);
+            } else {
+              TC_CYC(it, 8);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_tf32_ts(acc, a_hi + 8u * j, db + kAdv * j, idesc_ts, accum | (j > 0));
+              TC_CYC(it, 9);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_tf32_ts(acc, a_hi + 8u * j, lb + kAdv * j, idesc_ts, 1u);
+              TC_CYC(it, 10);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_tf32_ts(acc, a_lo + 8u * j, db + kAdv * j, idesc_ts, 1u);
+              TC_CYC(it, 11);
+              umma_commit(loe0 + 8u * ls);
+              TC_CYC(it, 2);
+              umma_commit(empty0 + 8u * st);
+              TC_CYC(it, 12);
+            }
+            accum = 1u;
+            if (++st == p.stages) { st = 0; ph ^= 1u; db = b_desc0; } else { db += st_step; }
+            if (++ls == p.lo_stages) { ls = 0; lph ^= 1u; lb = lb_desc0; a_hi = a_base; } else { lb += lo_step; a_hi += 64u; }
+          }
+          if (PAIR) umma_commit_2cta(smem_u32(&ctl->acc_full[ab]));
+          else umma_commit(smem_u32(&ctl->acc_full[ab]));
+          TC_STAMP(3);
+          u += kb - ka;
+        }
+      } else {
       int it = 0, seg = 0;
       for (int ph = 0; ph < so.n; ++ph)
       for (long long u = so.lo[ph], u_end = so.hi[ph]; u < u_end; ++seg) {
@@ -571,10 +647,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int k = ka; k < kb; ++k, ++it) {
           const int st = it % p.stages;
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          TC_CYC(it, 13);
           if (!PAIR) {  // (PAIR: the converters of both CTAs vouch for the tiles through conv[])
             mbar_wait(smem_u32(&ctl->full[st]), ph);
             tc_fence_after();
           }
+          TC_CYC(it, 14);
           if (it == 0) TC_STAMP(2);
           const uint32_t sa = stage_base + (uint32_t)st * stage_bytes;
           uint64_t da, db;
@@ -594,8 +672,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           if (p.passes == 3) {
             const int ls = it % p.lo_stages;
+            TC_CYC(it, 0);
             mbar_wait(smem_u32(&ctl->conv[ls]), (uint32_t)(it / p.lo_stages) & 1u);
             tc_fence_after();
+            TC_CYC(it, 1);
             if (it == 8) TC_STAMP(14);
             if (it == 9) TC_STAMP(15);
             const uint32_t sl = lo_base + (uint32_t)ls * lo_bytes;
@@ -614,107 +694,132 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 for (int j = 0; j < 4; ++j) umma_tf32_ts_2cta(acc, a_hi + 8u * j, lb + kadv * j, idesc_ts, 1u);
                 for (int j = 0; j < 4; ++j) umma_tf32_ts_2cta(acc, a_lo + 8u * j, db + kadv * j, idesc_ts, 1u);
               } else {
+                TC_CYC(it, 8);
                 for (int j = 0; j < 4; ++j)
                   umma_tf32_ts(acc, a_hi + 8u * j, db + kadv * j, idesc_ts, (k > ka || j > 0) ? 1u : 0u);
+                TC_CYC(it, 9);
                 for (int j = 0; j < 4; ++j) umma_tf32_ts(acc, a_hi + 8u * j, lb + kadv * j, idesc_ts, 1u);
+                TC_CYC(it, 10);
                 for (int j = 0; j < 4; ++j) umma_tf32_ts(acc, a_lo + 8u * j, db + kadv * j, idesc_ts, 1u);
+                TC_CYC(it, 11);
               }
             }
             if (PAIR) umma_commit_2cta(smem_u32(&ctl->lo_empty[ls]));
             else umma_commit(smem_u32(&ctl->lo_empty[ls]));
+            TC_CYC(it, 2);
           }
           if (PAIR) umma_commit_2cta(smem_u32(&ctl->empty[st]));
           else umma_commit(smem_u32(&ctl->empty[st]));
+          TC_CYC(it, 12);
         }
         if (PAIR) umma_commit_2cta(smem_u32(&ctl->acc_full[ab]));
         else umma_commit(smem_u32(&ctl->acc_full[ab]));
         TC_STAMP(3);
         u += kb - ka;
       }
+      }  // generic path
     }
   } else if (warp < 2 + kConvThreads / 32) {
     // ---------------- converters (3xTF32): lo = v - trunc_tf32(v) of every staged tile ----------------
+    // a_tmem: the two 4-warp groups take alternate stages, so two conversions are in flight -- one group's
+    // load -> split -> tcgen05.st / st.shared -> fence -> arrive chain (latency, not issue, bound) overlaps the other's.
     if (p.passes == 3) {
-      const int ct = (warp - 2) * 32 + lane;
-      const int n16 = (int)(raw_bytes >> 4);
       const int n_units = (int)(u_end - u_begin);
-      for (int it = 0; it < n_units; ++it) {
-        const int st = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        const int ls = it % p.lo_stages;
-        if (it == 8 && ct == 0) TC_STAMP(8);
-        mbar_wait(smem_u32(&ctl->lo_empty[ls]), ((uint32_t)(it / p.lo_stages) & 1u) ^ 1u);
-        if (it == 8 && ct == 0) TC_STAMP(9);
-        mbar_wait(smem_u32(&ctl->full[st]), ph);
-        if (it == 8 && ct == 0) TC_STAMP(10);
-        const uint8_t* raw = smem_raw + (stage_base - smem_u32(smem_raw)) + (size_t)st * stage_bytes;
-        uint8_t* lo = smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)ls * lo_bytes;
-        const float4* src;
-        float4* dst;
-        int n16c;
-        if (!p.a_tmem) {
-          src = reinterpret_cast<const float4*>(raw);
-          dst = reinterpret_cast<float4*>(lo);
-          n16c = n16;
-        } else {
-          const int half = (warp - 2) >> 2;  // two warps share a TMEM lane group: K columns [16*half, +16)
+      if (p.a_tmem) {
+        const int grp = (warp - 2) >> 2, gt = ((warp - 2) & 3) * 32 + lane;  // group, thread within the group (0..127)
+        constexpr int kGT = kConvThreads / 2;
+        const int n16b = (int)(p.b_bytes >> 4);
+        int st = grp % p.stages, ls = grp % p.lo_stages;
+        uint32_t ph = (uint32_t)(grp / p.stages) & 1u, lph = (uint32_t)(grp / p.lo_stages) & 1u;
+        for (int it = grp; it < n_units; it += 2) {
+          if (gt == 0) TC_CYC(it, 3);
+          mbar_wait(smem_u32(&ctl->lo_empty[ls]), lph ^ 1u);
+          if (gt == 0) TC_CYC(it, 4);
+          mbar_wait(smem_u32(&ctl->full[st]), ph);
+          if (gt == 0) TC_CYC(it, 5);
+          const uint8_t* raw = smem_raw + (stage_base - smem_u32(smem_raw)) + (size_t)st * stage_bytes;
+          float4* dst = reinterpret_cast<float4*>(smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)ls * lo_bytes);
+          const uint32_t ta = tmem + (uint32_t)(p.acc_bufs * p.BN) + (uint32_t)ls * 64u + ((uint32_t)((warp & 3) * 32) << 16);
           uint32_t hi[16], lw[16];
-          if (!WGRAD) {
-            // A: tile row m (128 B, 8 swizzled 16-byte chunks) -> TMEM lane m
-            const int m = (warp & 3) * 32 + lane;
-            const float4* arow = reinterpret_cast<const float4*>(raw + m * 128);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float4 v = arow[(half * 4 + c) ^ (m & 7)];
-              const float4 l = tf32_lo4(v);
-              hi[4 * c] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
-              hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
-              lw[4 * c] = __float_as_uint(l.x); lw[4 * c + 1] = __float_as_uint(l.y);
-              lw[4 * c + 2] = __float_as_uint(l.z); lw[4 * c + 3] = __float_as_uint(l.w);
-            }
-          } else {
-            // A^T: lane m = (job, channel); K = the 32 pixels of the box.  Box layout: pixel rows of 128 B whose
-            // 32-byte units are XOR-swizzled with (row & 3) (128B swizzle, 32-byte atoms)
-            const float* box = reinterpret_cast<const float*>(raw + (size_t)(warp & 3) * p.KP * 128);
+          for (int half = 0; half < 2; ++half) {  // K columns [16*half, +16) of this thread's TMEM lane
+            if (!WGRAD) {
+              // A: tile row m (128 B, 8 swizzled 16-byte chunks) -> TMEM lane m
+              const int m = (warp & 3) * 32 + lane;
+              const float4* arow = reinterpret_cast<const float4*>(raw + m * 128);
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk) {
-              const int k = half * 16 + kk;
-              const float v = box[k * 32 + ((((lane >> 3) ^ (k & 3)) << 3) | (lane & 7))];
-              hi[kk] = __float_as_uint(v);
-              lw[kk] = __float_as_uint(tf32_lo(v));
+              for (int c = 0; c < 4; ++c) {
+                const float4 v = arow[(half * 4 + c) ^ (m & 7)];
+                const float4 l = tf32_lo4(v);
+                hi[4 * c] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+                hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+                lw[4 * c] = __float_as_uint(l.x); lw[4 * c + 1] = __float_as_uint(l.y);
+                lw[4 * c + 2] = __float_as_uint(l.z); lw[4 * c + 3] = __float_as_uint(l.w);
+              }
+            } else {
+              // A^T: lane m = (job, channel); K = the 32 pixels of the box.  Box layout: pixel rows of 128 B whose
+              // 32-byte units are XOR-swizzled with (row & 3) (128B swizzle, 32-byte atoms)
+              const float* box = reinterpret_cast<const float*>(raw + (size_t)(warp & 3) * p.KP * 128);
+#pragma unroll
+              for (int kk = 0; kk < 16; ++kk) {
+                const int k = half * 16 + kk;
+                const float v = box[k * 32 + ((((lane >> 3) ^ (k & 3)) << 3) | (lane & 7))];
+                hi[kk] = __float_as_uint(v);
+                lw[kk] = __float_as_uint(tf32_lo(v));
+              }
             }
+            tmem_st16(ta + (uint32_t)half * 16u, hi);
+            tmem_st16(ta + 32u + (uint32_t)half * 16u, lw);
           }
-          const uint32_t ta = tmem + (uint32_t)(p.acc_bufs * p.BN) + (uint32_t)ls * 64u + (uint32_t)half * 16u +
-                              ((uint32_t)((warp & 3) * 32) << 16);
-          tmem_st16(ta, hi);
-          tmem_st16(ta + 32u, lw);
-          src = reinterpret_cast<const float4*>(raw + p.a_bytes);
-          dst = reinterpret_cast<float4*>(lo);
-          n16c = (int)(p.b_bytes >> 4);
-        }
-        int i = ct;
-        for (; i + 3 * kConvThreads < n16c; i += 4 * kConvThreads) {  // loads first: 4 independent LDS.128 in flight
-          const float4 v0 = src[i], v1 = src[i + kConvThreads], v2 = src[i + 2 * kConvThreads],
-                       v3 = src[i + 3 * kConvThreads];
-          dst[i] = tf32_lo4(v0);
-          dst[i + kConvThreads] = tf32_lo4(v1);
-          dst[i + 2 * kConvThreads] = tf32_lo4(v2);
-          dst[i + 3 * kConvThreads] = tf32_lo4(v3);
-        }
-        for (; i < n16c; i += kConvThreads) dst[i] = tf32_lo4(src[i]);
-        if (it == 8 && ct == 0) TC_STAMP(11);
-        if (p.a_tmem) {
+          const float4* src = reinterpret_cast<const float4*>(raw + p.a_bytes);
+          int i = gt;
+          for (; i + 3 * kGT < n16b; i += 4 * kGT) {  // loads first: 4 independent LDS.128 in flight
+            const float4 v0 = src[i], v1 = src[i + kGT], v2 = src[i + 2 * kGT], v3 = src[i + 3 * kGT];
+            dst[i] = tf32_lo4(v0);
+            dst[i + kGT] = tf32_lo4(v1);
+            dst[i + 2 * kGT] = tf32_lo4(v2);
+            dst[i + 3 * kGT] = tf32_lo4(v3);
+          }
+          for (; i < n16b; i += kGT) dst[i] = tf32_lo4(src[i]);
           tmem_st_wait();
           tc_fence_before();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(smem_u32(&ctl->conv[ls]), 0);  // the leader's barrier counts both CTAs
+            else mbar_arrive(smem_u32(&ctl->conv[ls]));
+          }
+          if (gt == 0) TC_CYC(it, 6);
+          st += 2; if (st >= p.stages) { st -= p.stages; ph ^= 1u; }
+          ls += 2; if (ls >= p.lo_stages) { ls -= p.lo_stages; lph ^= 1u; }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          if (PAIR) mbar_arrive_cluster(smem_u32(&ctl->conv[ls]), 0);  // the leader's barrier counts both CTAs
-          else mbar_arrive(smem_u32(&ctl->conv[ls]));
+      } else {
+        // wgrad with more than 32 pixels per stage: A and B low parts both go to the shared-memory lo ring
+        const int ct = (warp - 2) * 32 + lane;
+        const int n16 = (int)(raw_bytes >> 4);
+        int st = 0, ls = 0;
+        uint32_t ph = 0, lph = 0;
+        for (int it = 0; it < n_units; ++it) {
+          mbar_wait(smem_u32(&ctl->lo_empty[ls]), lph ^ 1u);
+          mbar_wait(smem_u32(&ctl->full[st]), ph);
+          const float4* src = reinterpret_cast<const float4*>(smem_raw + (stage_base - smem_u32(smem_raw)) + (size_t)st * stage_bytes);
+          float4* dst = reinterpret_cast<float4*>(smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)ls * lo_bytes);
+          int i = ct;
+          for (; i + 3 * kConvThreads < n16; i += 4 * kConvThreads) {
+            const float4 v0 = src[i], v1 = src[i + kConvThreads], v2 = src[i + 2 * kConvThreads],
+                         v3 = src[i + 3 * kConvThreads];
+            dst[i] = tf32_lo4(v0);
+            dst[i + kConvThreads] = tf32_lo4(v1);
+            dst[i + 2 * kConvThreads] = tf32_lo4(v2);
+            dst[i + 3 * kConvThreads] = tf32_lo4(v3);
+          }
+          for (; i < n16; i += kConvThreads) dst[i] = tf32_lo4(src[i]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&ctl->conv[ls]));
+          if (++st == p.stages) { st = 0; ph ^= 1u; }
+          if (++ls == p.lo_stages) { ls = 0; lph ^= 1u; }
         }
-        if (it == 8 && ct == 0) TC_STAMP(12);
-        if (it == 9 && ct == 0) TC_STAMP(13);
       }
     }
   } else {
@@ -1069,12 +1174,17 @@ bool finish_plan(Plan* pl, int passes, bool wgrad) {
     lo_slot = pl->a_tmem ? pl->b_bytes : raw;
     pl->lo_stages = 2;
     pl->acc_bufs = 2;
-    // pair launches with a long K loop: the cross-SM handshakes need the converters further ahead of the MMAs ->
-    // one accumulator, and its TMEM columns deepen the A ring (BN + 4 * 64 <= 512)
-    if (pl->pair && pl->a_tmem && pl->KU >= 32 && pl->U / pl->G >= 32 && pl->BN + 4 * 64 <= 512 &&
-        budget >= 4 * lo_slot + 3 * raw) {
-      pl->acc_bufs = 1;
-      pl->lo_stages = 4;
+    // Long K segments per CTA: ONE accumulator (the un-overlapped epilogue is noise next to >= 16 stages) and its
+    // TMEM columns go to a deeper A ring (BN + lo_stages*64 <= 512), so the converters run several stages ahead of
+    // the MMA thread instead of handing it each stage just in time.
+    {
+      const long long seg_units = pl->KU < pl->U / pl->G ? pl->KU : pl->U / pl->G;
+      if (pl->a_tmem && seg_units >= 16) {
+        int deep = (512 - pl->BN) / 64;
+        if (deep > 4) deep = 4;
+        while (deep > 2 && budget < deep * lo_slot + 3 * raw) --deep;
+        if (deep > 2) { pl->acc_bufs = 1; pl->lo_stages = deep; }
+      }
     }
     if (budget < pl->lo_stages * lo_slot + 2 * raw) return false;
     pl->stages = (int)((budget - pl->lo_stages * lo_slot) / raw);

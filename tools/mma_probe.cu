@@ -131,6 +131,35 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int mode, int niter, int 
     t1 = clock64();
     done = 1;
     if (blockIdx.x == 0) out[0] = t1 - t0;
+  } else if (hammer == 3 && threadIdx.x >= 32) {
+    const uint32_t ta = tmem_base + 448u + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+    uint32_t v = threadIdx.x;
+    while (!done) {
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+          ::"r"(ta), "r"(v) : "memory");
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+          ::"r"(ta + 16u), "r"(v) : "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      ++v;
+    }
+    if (v == 0x12345u) out[1] = 1;
+  } else if (hammer == 4 && threadIdx.x >= 32) {
+    // epilogue-like TMEM reads of an accumulator region
+    const uint32_t ta = tmem_base + 192u + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+    uint32_t sink = 0;
+    while (!done) {
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(ta) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      sink += r[0] + r[15];
+    }
+    if (sink == 0x12345u) out[1] = 1;
   } else if (hammer == 1 && threadIdx.x >= 32) {
     float4* reg = reinterpret_cast<float4*>(smem_raw + 1024 + 16384 + 32768);  // 32 KB scratch after A and B
     const int t = threadIdx.x - 32;
@@ -159,9 +188,9 @@ int main() {
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int niter = 4092 * 16;
   const char* names[8] = {"tf32 K-major SW128", "tf32 MN-major     ", "bf16 K-major SW128", "tf32 K-major SW32 ", "tf32 K-major SW64 ", "tf32 3x pattern   ", "3x, A from TMEM   ", "3x TMEM-A + commit"};
-  for (int mode : {5, 6, 7})
-    for (int N : {64, 128, 192}) {
-      for (int hammer : {0, 1}) {
+  for (int mode : {7})
+    for (int N : {128, 192}) {
+      for (int hammer : {0, 1, 3, 4}) {
         const int grid = 148;
         probe<<<grid, 128, 200 * 1024>>>(N, mode, niter, hammer, d);
         cudaError_t e = cudaDeviceSynchronize();

@@ -64,6 +64,20 @@ def main():
         print(f"rc={rc} event time {e0.elapsed_time(e1) * 1e3:.1f} us (incl. fix-up), {len(t)} CTAs; us since first CTA start:")
         for i, n in enumerate(names):
             print(f"  {n:11s} min {t[:, i].min():7.2f}  median {np.median(t[:, i]):7.2f}  max {t[:, i].max():7.2f}")
+        if hasattr(rt.lib.dll, "nvae_debug_tc_cycles"):
+            cb = (C.c_longlong * 128)()
+            rt.lib.dll.nvae_debug_tc_cycles(cb)
+            cy = np.array(cb, dtype=np.int64).reshape(8, 16)
+            base = cy[0, 0]
+            print("CTA 0, cycles since MMA thread reached unit 8 (units 8..15):")
+            print("  unit  mma:wait_conv  conv_ok  issued+commit | conv:begin  lo_empty_ok  full_ok  arrived")
+            for u in range(8):
+                r = cy[u] - base
+                print(f"  {u + 8:4d}  {r[0]:12d} {r[1]:8d} {r[2]:14d} | {r[3]:10d} {r[4]:12d} {r[5]:8d} {r[6]:8d}")
+            print("  unit  loop_top  full_ok  wait_conv  conv_ok  mma0  +4  +8  +12  commit1  commit2   (MMA thread, same origin)")
+            for u in range(8):
+                r = cy[u] - base
+                print(f"  {u + 8:4d}  {r[13]:8d} {r[14]:8d} {r[0]:9d} {r[1]:8d} {r[8]:6d} {r[9]:5d} {r[10]:5d} {r[11]:5d} {r[2]:8d} {r[12]:8d}")
 
 
 if __name__ == "__main__":
