@@ -288,9 +288,9 @@ def main():
     peak = bf16_peak / 2.0  # TF32 = half the bf16 rate (nominal ratio) of the measured/fallback bf16 burst figure
     achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01d_*.md);
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01h_ncu_*.md);
                 # algorithmic bytes are 127.9 MB (x + w + y once)
-                "traffic": 127.0e6 if x3 else None,
+                "traffic": 113.3e6 if x3 else None,
                 "mma_issue_factor": 3 if x3 else 1,
                 "note": ("3xTF32 issues 3 MMAs per algorithmic product, so its ceiling is peak/3; "
                          "frac is algorithmic FLOP/s over the full TF32 peak") if x3 else "",
