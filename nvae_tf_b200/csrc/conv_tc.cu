@@ -265,9 +265,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// index: operand (0 = A source 1, 1 = A source 2, 2 = B)
+// index: operand (0 = A source 1, 1 = A source 2, 2 = B); wgrad only: 3 = x and 4 = dy as 5-D "chunked" views
+// {32 ch, W, H, N, C/32} whose box takes several 32-channel chunks in ONE TMA instruction
 struct TmapSet {
-  CUtensorMap m[3];
+  CUtensorMap m[5];
 };
 
 struct TcParams {
@@ -293,6 +294,7 @@ struct TcParams {
   int8_t tap_dh[25], tap_dw[25];  // A box origin shift of k-loop tap i (rows / columns of the A pixel grid)
   int8_t tap_par[25];           // stride-2 forward: which (row parity*2 + column parity) plane of x the tap reads
   int8_t tap_w[25];             // weight tap (r*S+s) the k-loop tap i multiplies with
+  int x_chunked, dy_chunked;    // wgrad: the four x boxes / the BN/32 dy boxes of a stage come from one 5-D box each
   int a5d;                      // A maps are 5-D stride-2 views {2C, W/2, 2, H/2, N} of x (forward / wgrad of stride 2)
   int par_c;                    // ... channel offset of the odd-column plane (= Cin)
   int oH, oW, os, ooh, oow;     // output pixel of tile pixel (n,h,w): (n, h*os + ooh, w*os + oow) in an oH x oW image
@@ -536,6 +538,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
           }
           const uint32_t tx = (uint32_t)(njob + nb) * box_bytes;
+          // the tile's four jobs are consecutive channel chunks of ONE tap -> a single chunked box fetches them
+          const bool x_one = p.x_chunked && njob == 4 && (mt * 4) / nch == (mt * 4 + 3) / nch;
           for (int k = ka; k < kb; ++k, ++it) {
             int n0, h0;
             if (p.tn > 1) { n0 = k * p.tn; h0 = 0; }
@@ -546,12 +550,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t full = smem_u32(&ctl->full[st]);
             const uint32_t sa = stage_base + (uint32_t)st * stage_bytes;
             mbar_expect_tx(full, tx);
-            for (int j = 0; j < njob; ++j) {
-              if (p.a5d) tma_load_5d(sa + (uint32_t)j * box_bytes, &maps.m[0], full, jc[j], jw[j], jp[j], h0 + jh[j], n0);
-              else tma_load_4d(sa + (uint32_t)j * box_bytes, &maps.m[js[j]], full, jc[j], jw[j], h0 + jh[j], n0);
+            // (a wgrad stage used to be ten TMA instructions -- 4 x boxes + 6 dy boxes -- and was bound by their issue
+            // cost; the chunked 5-D views fetch each operand with one)
+            if (x_one) {
+              tma_load_5d(sa, &maps.m[3], full, 0, jw[0], h0 + jh[0], n0, jc[0] / kChunk);
+            } else {
+              for (int j = 0; j < njob; ++j) {
+                if (p.a5d) tma_load_5d(sa + (uint32_t)j * box_bytes, &maps.m[0], full, jc[j], jw[j], jp[j], h0 + jh[j], n0);
+                else tma_load_4d(sa + (uint32_t)j * box_bytes, &maps.m[js[j]], full, jc[j], jw[j], h0 + jh[j], n0);
+              }
             }
-            for (int b = 0; b < nb; ++b)
-              tma_load_4d(sa + p.a_bytes + (uint32_t)b * box_bytes, &maps.m[2], full, nt * p.BN + b * kChunk, 0, h0, n0);
+            if (p.dy_chunked) {
+              tma_load_5d(sa + p.a_bytes, &maps.m[4], full, 0, 0, h0, n0, nt * nb);
+            } else {
+              for (int b = 0; b < nb; ++b)
+                tma_load_4d(sa + p.a_bytes + (uint32_t)b * box_bytes, &maps.m[2], full, nt * p.BN + b * kChunk, 0, h0, n0);
+            }
           }
         }
         u += kb - ka;
@@ -1095,6 +1109,22 @@ int make_map_s2(CUtensorMap* m, const float* base, int N, int H, int W, int C, i
   return r == CUDA_SUCCESS ? NVAE_OK : NVAE_E_DRIVER;
 }
 
+// 5-D chunked view of an NHWC tensor view (C % 32 == 0): {32, W, H, N, C/32}; the box takes `nchunk` 32-channel chunks,
+// which land in shared memory chunk-major -- exactly the layout of `nchunk` separate 4-D boxes back to back.
+int make_map_chunked(CUtensorMap* m, const float* base, int N, int H, int W, int C, int ld, int tw, int th, int tn,
+                     int nchunk, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return NVAE_E_DRIVER;
+  cuuint64_t dims[5] = {(cuuint64_t)kChunk, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)(C / kChunk)};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4, (cuuint64_t)kChunk * 4};
+  cuuint32_t box[5] = {(cuuint32_t)kChunk, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn, (cuuint32_t)nchunk};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NVAE_OK : NVAE_E_DRIVER;
+}
+
 // Taps of a stride-2 backward-data launch for the output pixels of parity (a, b): dx[2h'+a, 2w'+b] sums
 // dy[h' + (a + pad_t - r)/2, w' + (b + pad_l - s)/2] * w[r, s] over the taps whose offsets are whole.
 struct TapList { int n; int8_t dh[25], dw[25], w[25]; };
@@ -1471,6 +1501,19 @@ int nvae_conv2d_wgrad_tc(const NvaeConvDesc* d, const float* x, const float* x2,
   if (rc) return rc;
   rc = make_map_nhwc(&maps.m[2], dy + d->y_off, d->N, d->Ho, d->Wo, d->Cout, ld, p.tw, p.th, p.tn, swz);
   if (rc) return rc;
+  maps.m[3] = maps.m[0];
+  maps.m[4] = maps.m[2];
+  // one TMA instruction per operand and stage where the channel counts allow the chunked view
+  p.x_chunked = d->stride == 1 && d->Cin2 == 0 && d->Cin % kChunk == 0 && d->Cin >= 4 * kChunk;
+  p.dy_chunked = d->Cout % kChunk == 0 && (ld % 4) == 0 && pl.BN % kChunk == 0 && d->Cout % pl.BN == 0;
+  if (p.x_chunked) {
+    rc = make_map_chunked(&maps.m[3], x, d->N, d->H, d->W, d->Cin, d->Cin, p.tw, p.th, p.tn, 4, swz);
+    if (rc) return rc;
+  }
+  if (p.dy_chunked) {
+    rc = make_map_chunked(&maps.m[4], dy + d->y_off, d->N, d->Ho, d->Wo, d->Cout, ld, p.tw, p.th, p.tn, pl.BN / kChunk, swz);
+    if (rc) return rc;
+  }
   return launch<true>(maps, p, pl, stream);
 }
 
