@@ -71,6 +71,15 @@ NVAE_API int nvae_bn_stats(const float* x, int64_t rows, int C, const float* gam
                   float* moving_mean, float* moving_var, int training, float momentum, float eps,
                   float* stat, void* ws, size_t ws_bytes, nvae_stream_t stream);
 
+/* nvae_bn_stats followed by nvae_bn_act_fwd (below) as ONE call: out = act(BN(x)) [-> nearest x2], stat and the moving
+ * statistics updated as by nvae_bn_stats.  Training-mode tensors that fit L2 run as a single thread-block-cluster
+ * launch (per-cluster DSMEM reduction of the statistics, apply pass re-reads from L1/L2); anything else is the two
+ * entry points back to back.  Replaces: BatchNormalization + activation pairs at common.py:166-167,
+ * encoder.py:102-104, decoder.py:139,143 (same semantics as the two calls it fuses). */
+NVAE_API int nvae_bn_fwd(const float* x, int64_t rows, int C, const float* gamma, const float* beta, float* moving_mean,
+                float* moving_var, int training, float momentum, float eps, float* stat, int act, int up_h, int up_w,
+                int round_tf32, float* out, void* ws, size_t ws_bytes, nvae_stream_t stream);
+
 /* out = act(x*scale+shift) (stat==NULL: out = act(x)); optional nearest x2 upsample
  * (tf.image.resize "nearest", common.py:168-172: pass up_h=H, up_w=W of x, else 0,0);
  * round_tf32!=0 rounds the result to TF32 (RN) so single-pass kind::tf32 consumes it without truncation bias. */

@@ -5,7 +5,19 @@
 // There is no CPU fallback anywhere: an unsupported descriptor is an error code.
 #include "conv_internal.h"
 
+#include <stdlib.h>
+#include <string.h>
+
 using namespace nvae;
+
+// NVAE_PDL=1 turns programmatic dependent launch on (read once; see common.cuh)
+bool nvae::pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("NVAE_PDL");
+    return e != nullptr && strcmp(e, "1") == 0;
+  }();
+  return on;
+}
 
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 

@@ -136,6 +136,7 @@ struct WgradProb {
 
 template <class Prob>
 __global__ void __launch_bounds__(kSimtThreads) simt_conv_kernel(const Prob p, int64_t k_total, int64_t k_per_split) {
+  nvae::pdl_enter();
   __shared__ float As[kBK][kBM + 4];
   __shared__ float Bs[kBK][kBN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(kSimtThreads) simt_conv_kernel(const Prob p, i
 // column sums of a [rows, C] matrix, deterministic two-stage
 __global__ void colsum_partial_kernel(const float* __restrict__ a, int64_t rows, int C, int ld, int64_t rows_per_split,
                                       float* __restrict__ part) {
+  nvae::pdl_enter();
   __shared__ float sm[8][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
@@ -215,6 +217,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ a, int64_t rows,
   }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, int nsplit, int C, float* __restrict__ out) {
+  nvae::pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
@@ -257,9 +260,9 @@ int nvae_colsum(const float* a, int64_t rows, int C, int ld, float* out, void* w
   nsplit = ceil_div(rows, rps);
   if (ws == nullptr || ws_bytes < (size_t)nsplit * C * sizeof(float)) return NVAE_E_WORKSPACE;
   float* part = reinterpret_cast<float*>(ws);
-  colsum_partial_kernel<<<dim3((C + 31) / 32, (unsigned)nsplit), 256, 0, stream>>>(a, rows, C, ld, rps, part);
+  nvae::launch(colsum_partial_kernel, dim3((C + 31) / 32, (unsigned)nsplit), 256, 0, stream, a, rows, C, ld, rps, part);
   NVAE_RETURN_IF_LAUNCH_FAILED();
-  colsum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, (int)nsplit, C, out);
+  nvae::launch(colsum_final_kernel, (C + 127) / 128, 128, 0, stream, part, (int)nsplit, C, out);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -271,6 +274,7 @@ size_t nvae_colsum_ws_bytes(int C) { return (size_t)256 * C * sizeof(float); }
 __global__ void __launch_bounds__(256) conv_head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ bias, float* __restrict__ y, int N,
                                                             int H, int W, int C, int R, int S, int pad_t, int pad_l) {
+  nvae::pdl_enter();
   extern __shared__ float wsm[];  // [R*S][C]
   for (int i = threadIdx.x; i < R * S * C; i += blockDim.x) wsm[i] = w[i];
   __syncthreads();
@@ -314,7 +318,7 @@ int nvae_conv2d_fwd_simt(const NvaeConvDesc* d, const float* x, const float* x2,
     const int64_t npix = (int64_t)d->N * d->H * d->W;
     int64_t grid = ceil_div(npix, 32);
     if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-    conv_head_fwd_kernel<<<(int)grid, 256, (size_t)d->R * d->S * d->Cin * sizeof(float), stream>>>(
+    nvae::launch(conv_head_fwd_kernel, (int)grid, 256, (size_t)d->R * d->S * d->Cin * sizeof(float), stream, 
         x, w, bias, y, d->N, d->H, d->W, d->Cin, d->R, d->S, d->pad_t, d->pad_l);
     NVAE_RETURN_IF_LAUNCH_FAILED();
     return NVAE_OK;
@@ -326,7 +330,7 @@ int nvae_conv2d_fwd_simt(const NvaeConvDesc* d, const float* x, const float* x2,
   p.K = d->R * d->S * p.g.Ct;
   p.Nn = d->Cout;
   dim3 grid((unsigned)ceil_div(p.M, kBM), (unsigned)ceil_div(p.Nn, kBN), 1);
-  simt_conv_kernel<FwdProb><<<grid, kSimtThreads, 0, stream>>>(p, p.K, p.K);
+  nvae::launch(simt_conv_kernel<FwdProb>, grid, kSimtThreads, 0, stream, p, p.K, p.K);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -340,7 +344,7 @@ int nvae_conv2d_dgrad_simt(const NvaeConvDesc* d, const float* dy, const float* 
   p.K = d->R * d->S * d->Cout;
   p.Nn = p.g.Ct;
   dim3 grid((unsigned)ceil_div(p.M, kBM), (unsigned)ceil_div(p.Nn, kBN), 1);
-  simt_conv_kernel<DgradProb><<<grid, kSimtThreads, 0, stream>>>(p, p.K, p.K);
+  nvae::launch(simt_conv_kernel<DgradProb>, grid, kSimtThreads, 0, stream, p, p.K, p.K);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -366,6 +370,7 @@ size_t nvae_conv2d_wgrad_simt_ws_bytes(const NvaeConvDesc* d) {
 }
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int64_t n, int splits, float* __restrict__ dw) {
+  nvae::pdl_enter();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += part[(int64_t)k * n + i];
@@ -389,13 +394,13 @@ int nvae_conv2d_wgrad_simt(const NvaeConvDesc* d, const float* x, const float* x
     p.dw = reinterpret_cast<float*>(ws);
   }
   dim3 grid((unsigned)ceil_div(p.M, kBM), (unsigned)ceil_div(p.Nn, kBN), (unsigned)splits);
-  simt_conv_kernel<WgradProb><<<grid, kSimtThreads, 0, stream>>>(p, p.Kpix, kps);
+  nvae::launch(simt_conv_kernel<WgradProb>, grid, kSimtThreads, 0, stream, p, p.Kpix, kps);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   if (p.split) {
     const int64_t n = (int64_t)p.M * p.Nn;
     int64_t g = ceil_div(n, 256);
     if (g > kNumSMs * 8) g = kNumSMs * 8;
-    wgrad_reduce_kernel<<<(int)g, 256, 0, stream>>>(p.dw, n, (int)splits, dw);
+    nvae::launch(wgrad_reduce_kernel, (int)g, 256, 0, stream, p.dw, n, (int)splits, dw);
     NVAE_RETURN_IF_LAUNCH_FAILED();
   }
   return NVAE_OK;

@@ -27,6 +27,7 @@
 // warps 2..9 = lo-part converters, warps 10..13 = epilogue (tcgen05.ld -> bias / residual / accumulate ->
 // 128-bit stores) on a double-buffered TMEM accumulator, so the next tile's MMAs overlap the drain.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -123,6 +124,17 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 (fp16 operands, fp32 accumulate), A from TMEM: lanes = rows, each 32-bit column holds two consecutive K
+// elements (even k in the low half); one instruction covers K = 16, i.e. 8 columns
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // 16 consecutive 32-bit columns of this thread's TMEM lane <- registers
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
@@ -206,7 +218,10 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int n, int a_mn_major, int b
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-
+// D=F32, A=B=F16 (format 0), K-major A (TMEM), M=128, N=n
+__host__ __device__ inline uint32_t umma_idesc_f16(int n, int b_mn_major, int m = kBM) {
+  return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 #ifdef NVAE_TC_TIMING
 // development build only: per-CTA timestamps (ns, %globaltimer) [start, setup done, first tile landed, last MMA
@@ -282,6 +297,13 @@ struct TcParams {
   int n_mtiles;                 // 128-row M tiles of the problem (a pair's second tile may lie beyond it)
   int a_tmem;                   // 3xTF32: A (high and low parts) is staged in TMEM by the converters, only B lo in smem
   int BN, stages, lo_stages, passes;  // raw-tile ring, lo-tile ring (3xTF32 only); passes: 1 = TF32, 3 = 3xTF32
+  int f16;                      // 3xFP16 (forward / dgrad, a_tmem): both operands are scaled by a power of two that
+                                // puts their absmax in [2^14, 2^15), split into fp16 high + low parts by the converters
+                                // (A by the converters -> TMEM; B by a pack kernel ahead of the launch, 128-byte rows of
+                                // [hi 32 x fp16 | lo 32 x fp16] per 32-deep K chunk that TMA drops into the raw ring) and multiplied
+                                // as hi*hi + hi*lo + lo*hi with kind::f16 -- the same 22 significant bits per operand
+                                // as 3xTF32 at twice the tensor-pipe rate; the epilogue undoes the scales
+  const float* amax;            // device: {absmax(A operand), absmax(B operand)}, written just before the launch
   int n_ntiles;                 // tile t = mt * n_ntiles + nt
   int KU;                       // k-units (pipeline stages) per tile
   int T;                        // tiles
@@ -381,9 +403,10 @@ __device__ __forceinline__ RowCtx row_ctx(const TcParams& p, int mt, int row) {
 
 // final store of 4 consecutive columns starting at tile column `col` (multiple of 4)
 template <bool WGRAD>
-__device__ __forceinline__ void store4(const TcParams& p, const RowCtx& r, int nt, int col, float4 o) {
+__device__ __forceinline__ void store4(const TcParams& p, const RowCtx& r, int nt, int col, float4 o, float oscale) {
   const int n = nt * p.BN + col;
   if (!r.ok || col >= p.BN) return;
+  if (p.f16) { o.x *= oscale; o.y *= oscale; o.z *= oscale; o.w *= oscale; }
   if (WGRAD) {
     if (n >= p.Cout) return;
     stg4(p.out1 + r.base * p.Cout + n, o);
@@ -419,6 +442,35 @@ __device__ __forceinline__ float4 tf32_lo4(const float4& v) {
   return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
 }
 
+// ---- 3xFP16: power-of-two operand scales from the absmax values ------------------------------------------
+// absmax = m * 2^e (m in [0.5, 1)) -> scale 2^(15 - e): the scaled absmax lies in [2^14, 2^15), inside fp16's range
+// (max 65504) with its low part 2^-11 below still normal down to elements 2^-18 of the absmax
+__device__ __forceinline__ int f16_exp(float amax) {
+  int e = 0;
+  if (amax > 0.f && amax < 3.0e38f) (void)frexpf(amax, &e);
+  return e;
+}
+__device__ __forceinline__ float f16_in_scale(float amax) { return amax > 0.f ? ldexpf(1.f, 15 - f16_exp(amax)) : 1.f; }
+__device__ __forceinline__ float f16_out_scale(const float* amax) {
+  const float a = __ldg(amax), b = __ldg(amax + 1);
+  return ldexpf(1.f, (a > 0.f ? f16_exp(a) - 15 : 0) + (b > 0.f ? f16_exp(b) - 15 : 0));
+}
+// 8 consecutive K elements -> packed fp16 high parts (RN) and low parts rn(v - hi)
+__device__ __forceinline__ void f16_split8(const float4& v0, const float4& v1, float s, uint4& hi, uint4& lo) {
+  const float a[8] = {v0.x * s, v0.y * s, v0.z * s, v0.w * s, v1.x * s, v1.y * s, v1.z * s, v1.w * s};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(a[2 * i], a[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(a[2 * i] - hf.x, a[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -428,6 +480,7 @@ __device__ __forceinline__ float4 tf32_lo4(const float4& v) {
 // read by the MMAs -- the shared-memory port, not the tensor pipe, is what bounds the single-CTA kernel.
 template <bool WGRAD, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
+  nvae::pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_raw);
   const uint32_t stage_base = (smem_u32(smem_raw) + (uint32_t)sizeof(SmemCtl) + 1023u) & ~1023u;
@@ -436,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   // lo ring.  a_tmem: [B lo] only -- A's high and low parts go to TMEM; else (wgrad with > 32 pixels per stage)
   // [A lo][B lo] per slot
   const uint32_t lo_base = stage_base + (uint32_t)p.stages * raw_bytes;
-  const uint32_t lo_bytes = p.a_tmem ? p.b_bytes : raw_bytes;
+  const uint32_t lo_bytes = p.f16 ? 0u : (p.a_tmem ? p.b_bytes : raw_bytes);  // 3xFP16: B arrives pre-split, no lo ring
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // PAIR: the work unit space is over 256-row pair tiles and is cut over gridDim.x / 2 pairs
   const int G = PAIR ? gridDim.x >> 1 : gridDim.x, cta = PAIR ? blockIdx.x >> 1 : blockIdx.x;
@@ -473,6 +526,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything arrives on them remotely
   tc_fence_after();
+  nvae::pdl_wait();  // barrier init, TMEM allocation and descriptor prefetch overlap the previous kernel's tail
   const uint32_t tmem = ctl->tmem_base;
   if (threadIdx.x == 0) TC_STAMP(1);
 
@@ -596,6 +650,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         uint32_t ph = 0, lph = 0, a_hi = a_base;
         uint64_t db = b_desc0, lb = lb_desc0;
         (void)it;
+        const bool f16 = !WGRAD && !PAIR && p.f16;
+        const uint32_t idesc_h = umma_idesc_f16(p.BN, 0);
+        const uint32_t a_slot = f16 ? 32u : 64u;  // TMEM columns per A ring slot
         for (int sp = 0; sp < so.n; ++sp)
         for (long long u = so.lo[sp], u_end = so.hi[sp]; u < u_end; ++seg) {
           const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
@@ -613,8 +670,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tc_fence_after();
             TC_CYC(it, 1);
             if (it == 0) TC_STAMP(2);
-            const uint32_t a_lo = a_hi + 32u;
-            if (PAIR) {
+            const uint32_t a_lo = a_hi + (f16 ? 16u : 32u);
+            if (f16) {
+              // pre-split B row (TMA, raw ring): [hi k0..15 | hi k16..31 | lo k0..15 | lo k16..31], 32 bytes each
+              TC_CYC(it, 8);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + 2u * j, idesc_h, accum | (j > 0));
+              TC_CYC(it, 9);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + 4u + 2u * j, idesc_h, 1u);
+              TC_CYC(it, 10);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_lo + 8u * j, db + 2u * j, idesc_h, 1u);
+              TC_CYC(it, 11);
+              umma_commit(loe0 + 8u * ls);
+              TC_CYC(it, 2);
+              umma_commit(empty0 + 8u * st);
+              TC_CYC(it, 12);
+            } else if (PAIR) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) umma_tf32_ts_2cta(acc, a_hi + 8u * j, db + kAdv * j, idesc_ts, accum | (j > 0));
 #pragma unroll
@@ -641,7 +714,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             accum = 1u;
             if (++st == p.stages) { st = 0; ph ^= 1u; db = b_desc0; } else { db += st_step; }
-            if (++ls == p.lo_stages) { ls = 0; lph ^= 1u; lb = lb_desc0; a_hi = a_base; } else { lb += lo_step; a_hi += 64u; }
+            if (++ls == p.lo_stages) { ls = 0; lph ^= 1u; lb = lb_desc0; a_hi = a_base; } else { lb += lo_step; a_hi += a_slot; }
           }
           if (PAIR) umma_commit_2cta(smem_u32(&ctl->acc_full[ab]));
           else umma_commit(smem_u32(&ctl->acc_full[ab]));
@@ -745,6 +818,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int n16b = (int)(p.b_bytes >> 4);
         int st = grp % p.stages, ls = grp % p.lo_stages;
         uint32_t ph = (uint32_t)(grp / p.stages) & 1u, lph = (uint32_t)(grp / p.lo_stages) & 1u;
+        const float f16_sa = p.f16 ? f16_in_scale(__ldg(p.amax)) : 1.f;
         for (int it = grp; it < n_units; it += 2) {
           if (gt == 0) TC_CYC(it, 3);
           mbar_wait(smem_u32(&ctl->lo_empty[ls]), lph ^ 1u);
@@ -753,6 +827,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (gt == 0) TC_CYC(it, 5);
           const uint8_t* raw = smem_raw + (stage_base - smem_u32(smem_raw)) + (size_t)st * stage_bytes;
           float4* dst = reinterpret_cast<float4*>(smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)ls * lo_bytes);
+          if (!WGRAD && !PAIR && p.f16) {
+            // ---- 3xFP16: scale, split into fp16 high / low parts -> TMEM (16 + 16 packed columns); B arrives pre-split ----
+            const uint32_t ta = tmem + (uint32_t)(p.acc_bufs * p.BN) + (uint32_t)ls * 32u + ((uint32_t)((warp & 3) * 32) << 16);
+            {
+              const int m = (warp & 3) * 32 + lane;
+              const float4* arow = reinterpret_cast<const float4*>(raw + m * 128);
+              uint32_t hi[16], lw[16];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint4 h, l;
+                f16_split8(arow[(2 * c) ^ (m & 7)], arow[(2 * c + 1) ^ (m & 7)], f16_sa, h, l);
+                hi[4 * c] = h.x; hi[4 * c + 1] = h.y; hi[4 * c + 2] = h.z; hi[4 * c + 3] = h.w;
+                lw[4 * c] = l.x; lw[4 * c + 1] = l.y; lw[4 * c + 2] = l.z; lw[4 * c + 3] = l.w;
+              }
+              tmem_st16(ta, hi);
+              tmem_st16(ta + 16u, lw);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ctl->conv[ls]));
+            st += 2; if (st >= p.stages) { st -= p.stages; ph ^= 1u; }
+            ls += 2; if (ls >= p.lo_stages) { ls -= p.lo_stages; lph ^= 1u; }
+            continue;
+          }
           const uint32_t ta = tmem + (uint32_t)(p.acc_bufs * p.BN) + (uint32_t)ls * 64u + ((uint32_t)((warp & 3) * 32) << 16);
           uint32_t hi[16], lw[16];
 #pragma unroll
@@ -840,6 +940,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ---------------- epilogue: TMEM -> registers -> smem transpose -> global (final tile or raw partial) ----
     const int lg = warp & 3;  // TMEM lane group this warp may read: lanes [32*lg, +32)
     const int row = lg * 32 + lane;
+    const float oscale = p.f16 ? f16_out_scale(p.amax) : 1.f;
     EpiSmem* epi = reinterpret_cast<EpiSmem*>(smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)p.lo_stages * lo_bytes);
     const int q = lane & 7, r0 = lane >> 3;
     int seg = 0;
@@ -878,7 +979,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             RowCtx rc;
             rc.base = epi->rowbase[lg * 32 + r];
             rc.ok = rc.base >= 0;
-            store4<WGRAD>(p, rc, nt, col, o);
+            store4<WGRAD>(p, rc, nt, col, o, oscale);
           } else if (col < p.BN) {
             stg4(pdst + (int64_t)r * p.BN + col, o);
           }
@@ -922,7 +1023,9 @@ constexpr int kFixMaxGroups = 8;
 template <bool WGRAD>
 __global__ void __launch_bounds__(kFixThreads) conv_tc_fixup_kernel(const TcParams p, int G, int rows,
                                                                     const FixList fl) {
+  nvae::pdl_enter();
   __shared__ float4 red[kFixThreads];
+  const float oscale = p.f16 ? f16_out_scale(p.amax) : 1.f;
   const int c = fl.cta[blockIdx.x];
   const long long u0 = cta_u0(p, c, G), u1 = cta_u0(p, c + 1, G);
   const int t = (int)(u0 / p.KU);
@@ -967,7 +1070,7 @@ __global__ void __launch_bounds__(kFixThreads) conv_tc_fixup_kernel(const TcPara
         const int i = i0 + j * kFixThreads;
         if (i < total) {
           const int row = blockIdx.y * rows + i / bn4, col = (i % bn4) * 4;
-          store4<WGRAD>(p, row_ctx<WGRAD>(p, mt, row), nt, col, s[j]);
+          store4<WGRAD>(p, row_ctx<WGRAD>(p, mt, row), nt, col, s[j], oscale);
         }
       }
     }
@@ -998,15 +1101,69 @@ __global__ void __launch_bounds__(kFixThreads) conv_tc_fixup_kernel(const TcPara
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     const int row = blockIdx.y * rows + e / bn4, col = (e % bn4) * 4;
-    store4<WGRAD>(p, row_ctx<WGRAD>(p, mt, row), nt, col, s);
+    store4<WGRAD>(p, row_ctx<WGRAD>(p, mt, row), nt, col, s, oscale);
   }
 }
 
 __global__ void round_tf32_kernel(float* __restrict__ p, int64_t n4) {
+  nvae::pdl_enter();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = *reinterpret_cast<float4*>(p + 4 * i);
     v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
     stg4(p + 4 * i, v);
+  }
+}
+
+// absmax of two fp32 tensors in one launch (3xFP16 operand scales): blocks [0, g0) reduce a, the rest b; the result
+// slots are zeroed by a memset node ahead of the launch.  max is order-independent, so the atomics stay deterministic
+// (bit patterns of non-negative floats are monotonic as unsigned integers).
+__global__ void __launch_bounds__(256) absmax2_kernel(const float* __restrict__ a, int64_t na4, const float* __restrict__ b,
+                                                      int64_t nb4, int g0, unsigned* __restrict__ out) {
+  nvae::pdl_enter();
+  const bool second = (int)blockIdx.x >= g0;
+  const float* p = second ? b : a;
+  const int64_t n4 = second ? nb4 : na4;
+  const int64_t nblk = second ? (int64_t)gridDim.x - g0 : g0, blk = second ? (int64_t)blockIdx.x - g0 : blockIdx.x;
+  float m = 0.f;
+  const int64_t stride = nblk * 256;
+  int64_t i = blk * 256 + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    const float4 v0 = ldg4(p + 4 * i), v1 = ldg4(p + 4 * (i + stride)), v2 = ldg4(p + 4 * (i + 2 * stride)),
+                 v3 = ldg4(p + 4 * (i + 3 * stride));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v2.x), fabsf(v2.y)), fmaxf(fabsf(v2.z), fabsf(v2.w))));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v3.x), fabsf(v3.y)), fmaxf(fabsf(v3.z), fabsf(v3.w))));
+  }
+  for (; i < n4; i += stride) {
+    const float4 v = ldg4(p + 4 * i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  m = warp_max(m);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    m = warp_max(m);
+    if (threadIdx.x == 0) atomicMax(out + (second ? 1 : 0), __float_as_uint(m));
+  }
+}
+
+// 3xFP16 B operand: every 32-float K chunk (128 bytes) of the weight matrix becomes 128 bytes of
+// [32 fp16 high parts | 32 fp16 low parts] of the scaled values, so the SAME 2-D tensor map / box / swizzle that
+// stages the fp32 matrix stages the split operand.  One thread per 8 K elements.
+__global__ void __launch_bounds__(256) f16_pack_b_kernel(const float* __restrict__ w, int64_t n8,
+                                                         const float* __restrict__ amax, uint4* __restrict__ out) {
+  nvae::pdl_enter();
+  const float s = f16_in_scale(__ldg(amax + 1));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = i >> 2;
+    const int j = (int)(i & 3);
+    uint4 h, l;
+    f16_split8(ldg4(w + i * 8), ldg4(w + i * 8 + 4), s, h, l);
+    out[q * 8 + j] = h;
+    out[q * 8 + 4 + j] = l;
   }
 }
 
@@ -1161,7 +1318,8 @@ bool common_ok(const NvaeConvDesc* d, int which) {
 // Launch plan shared by the three directions: tiles, stages, stream-K grid, partial-buffer size.
 struct Plan {
   PixTile t;
-  int BN, stages, lo_stages, a_tmem, acc_bufs, pair, n_mtiles, n_ntiles, KU, G, njobs;
+  int BN, stages, lo_stages, a_tmem, acc_bufs, pair, n_mtiles, n_ntiles, KU, G, njobs, f16;
+  size_t pack_bytes;   // 3xFP16: the split B operand (same bytes as the fp32 weights) + 256 for the absmax slots, behind the partials
   uint32_t a_bytes, b_bytes;
   long long U;
   int whole_tiles;
@@ -1179,7 +1337,7 @@ bool finish_plan(Plan* pl, int passes, bool wgrad) {
   const int workers = pl->pair ? kNumSMs / 2 : kNumSMs;
   const long long T = (long long)(pl->pair ? (pl->n_mtiles + 1) / 2 : pl->n_mtiles) * pl->n_ntiles;
   pl->U = T * pl->KU;
-  const double t_unit = passes == 3 ? 0.95 : 0.35;
+  const double t_unit = passes == 3 ? (pl->f16 ? 0.5 : 0.95) : 0.35;
   const double slot_us = (double)kBM * pl->BN * 4 * 2 / 3.0e6;  // one partial written + read back
   pl->whole_tiles = 1;
   pl->G = (int)(T < workers ? T : workers);
@@ -1201,7 +1359,7 @@ bool finish_plan(Plan* pl, int passes, bool wgrad) {
   size_t lo_slot = 0;
   if (passes == 3) {  // raw ring for the TMA latency + a double-buffered lo ring (wgrad: A and B; fwd/dgrad: B only)
     pl->a_tmem = (!wgrad || pl->a_bytes == 4u * 32u * 128u) ? 1 : 0;  // wgrad: 32 pixels per stage fit the TMEM A ring
-    lo_slot = pl->a_tmem ? pl->b_bytes : raw;
+    lo_slot = pl->f16 ? 0 : (pl->a_tmem ? pl->b_bytes : raw);
     pl->lo_stages = 2;
     pl->acc_bufs = 2;
     // Long K segments per CTA: ONE accumulator (the un-overlapped epilogue is noise next to >= 16 stages) and its
@@ -1210,8 +1368,8 @@ bool finish_plan(Plan* pl, int passes, bool wgrad) {
     {
       const long long seg_units = pl->KU < pl->U / pl->G ? pl->KU : pl->U / pl->G;
       if (pl->a_tmem && seg_units >= 16) {
-        int deep = (512 - pl->BN) / 64;
-        if (deep > 4) deep = 4;
+        int deep = (512 - pl->BN) / (pl->f16 ? 32 : 64);
+        if (deep > (pl->f16 ? 6 : 4)) deep = pl->f16 ? 6 : 4;
         while (deep > 2 && budget < deep * lo_slot + 3 * raw) --deep;
         if (deep > 2) { pl->acc_bufs = 1; pl->lo_stages = deep; }
       }
@@ -1242,10 +1400,26 @@ bool pair_enabled() {
   return on;
 }
 
+// 3xFP16 instead of 3xTF32 (NVAE_PREC_TF32X3 only; same accuracy class, twice the MMA rate, but two extra passes over
+// the operands for their absmax): taken by the large GEMMs, where the MMAs are what the time goes to.
+// NVAE_F16X3=0 disables it, NVAE_F16X3_MIN_GFLOP moves the threshold (tests set 0 to cover small shapes).
+bool use_f16x3(const NvaeConvDesc* d, int which) {
+  if (d->precision != NVAE_PREC_TF32X3 || which == 2 || d->stride != 1 || d->Cin2 != 0) return false;
+  if (d->y_off != 0 || (d->y_ld != 0 && d->y_ld != d->Cout)) return false;
+  if ((which == 0 ? d->Cin : d->Cout) % kChunk != 0) return false;  // whole 32-deep K chunks (the packed B rows)
+  const char* e = getenv("NVAE_F16X3");
+  if (e != nullptr && e[0] == '0') return false;
+  const char* m = getenv("NVAE_F16X3_MIN_GFLOP");
+  const double min_gflop = m != nullptr ? atof(m) : 20.0;
+  const double gflop = 2.0 * d->N * d->Ho * d->Wo * (double)d->Cout * d->Cin * d->R * d->S * 1e-9;
+  return gflop >= min_gflop;
+}
+
 // which: 0 forward, 1 dgrad; ntaps: K-loop taps (a stride-2 dgrad launch covers one output parity class)
 bool plan_gemm(const NvaeConvDesc* d, int which, int ntaps, Plan* pl) {
   if (!common_ok(d, which) || !pick_pix_tile(d->N, d->Ho, d->Wo, kBM, 1, &pl->t)) return false;
   const int passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
+  pl->f16 = use_f16x3(d, which) && !pair_enabled();
   const int Ct = d->Cin + d->Cin2;
   const int n_total = which == 0 ? d->Cout : Ct;
   pl->n_mtiles = pl->t.n_tiles;
@@ -1258,12 +1432,19 @@ bool plan_gemm(const NvaeConvDesc* d, int which, int ntaps, Plan* pl) {
   pl->a_bytes = kBM * 128;
   pl->b_bytes = (uint32_t)(pl->pair ? pl->BN / 2 : pl->BN) * 128;  // pair: each CTA stages half of the B tile
   pl->njobs = 0;
-  return finish_plan(pl, passes, false);
+  if (!finish_plan(pl, passes, false)) return false;
+  pl->pack_bytes = 0;
+  if (pl->f16) {
+    pl->pack_bytes = al256((size_t)d->R * d->S * Ct * d->Cout * sizeof(float)) + 256;
+    pl->part_bytes += pl->pack_bytes;
+  }
+  return true;
 }
 
 bool plan_wgrad(const NvaeConvDesc* d, Plan* pl) {
   if (!common_ok(d, 2)) return false;
   pl->pair = 0;
+  pl->f16 = 0;
   const int passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
   if (!pick_pix_tile(d->N, d->Ho, d->Wo, 32, 8, &pl->t) && !pick_pix_tile(d->N, d->Ho, d->Wo, 64, 8, &pl->t) &&
       !pick_pix_tile(d->N, d->Ho, d->Wo, 128, 8, &pl->t))
@@ -1288,11 +1469,31 @@ void fill_common(TcParams* p, const NvaeConvDesc* d, const Plan& pl, float* part
   p->oH = d->Ho; p->oW = d->Wo; p->os = 1; p->ooh = 0; p->oow = 0;
   p->a5d = 0; p->par_c = d->Cin;
   p->tw = pl.t.tw; p->th = pl.t.th; p->tn = pl.t.tn; p->tiles_h = pl.t.tiles_h;
-  p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->acc_bufs = pl.acc_bufs; p->pair = pl.pair; p->n_mtiles = pl.n_mtiles; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
+  p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->acc_bufs = pl.acc_bufs; p->pair = pl.pair; p->n_mtiles = pl.n_mtiles; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1; p->f16 = pl.f16; p->amax = nullptr;
   p->n_ntiles = pl.n_ntiles; p->KU = pl.KU; p->U = pl.U;
   p->T = (pl.pair ? (pl.n_mtiles + 1) / 2 : pl.n_mtiles) * pl.n_ntiles; p->whole_tiles = pl.whole_tiles;
   p->a_bytes = pl.a_bytes; p->b_bytes = pl.b_bytes;
   p->part = part;
+}
+
+// 3xFP16 operand preparation on the launch stream: absmax of both operands (memset node + one launch), then the
+// split B operand.  Workspace behind the partials: [packed B][256 B: absmax slots].  Returns the packed B in *bc.
+int f16_prepare(TcParams* p, const Plan& pl, const float* a, int64_t na, const float* b, int64_t nb, void* ws,
+                cudaStream_t stream, const float** bc) {
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws) + pl.part_bytes - pl.pack_bytes;
+  unsigned* slot = reinterpret_cast<unsigned*>(base + pl.pack_bytes - 256);
+  cudaError_t e = cudaMemsetAsync(slot, 0, 2 * sizeof(unsigned), stream);
+  if (e != cudaSuccess) return (int)e;
+  auto blocks = [](int64_t n, int per) { int64_t g = ceil_div(n, per); return (int)(g < 1 ? 1 : (g > 4 * kNumSMs ? 4 * kNumSMs : g)); };
+  const int g0 = blocks(na / 4, 256 * 8), g1 = blocks(nb / 4, 256 * 8);
+  nvae::launch(absmax2_kernel, g0 + g1, 256, 0, stream, a, na / 4, b, nb / 4, g0, slot);
+  NVAE_RETURN_IF_LAUNCH_FAILED();
+  nvae::launch(f16_pack_b_kernel, blocks(nb / 8, 256 * 2), 256, 0, stream, b, nb / 8, reinterpret_cast<const float*>(slot),
+               reinterpret_cast<uint4*>(base));
+  NVAE_RETURN_IF_LAUNCH_FAILED();
+  p->amax = reinterpret_cast<const float*>(slot);
+  *bc = reinterpret_cast<const float*>(base);
+  return NVAE_OK;
 }
 
 template <bool WGRAD, bool PAIR>
@@ -1304,7 +1505,7 @@ int launch_main(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStre
     attr_done = true;
   }
   if (!PAIR) {
-    conv_tc_kernel<WGRAD, PAIR><<<pl.G, kThreads, pl.smem, stream>>>(maps, p);
+    nvae::launch(conv_tc_kernel<WGRAD, PAIR>, pl.G, kThreads, pl.smem, stream, maps, p);
     NVAE_RETURN_IF_LAUNCH_FAILED();
     return NVAE_OK;
   }
@@ -1342,7 +1543,7 @@ int launch(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t 
       const int nrk = pl.pair ? 2 : 1;
       int rows = 32;
       while (rows > 1 && (long long)fl.n * nrk * (kBM / rows) < 2 * kNumSMs) rows >>= 1;
-      conv_tc_fixup_kernel<WGRAD><<<dim3(fl.n, kBM / rows, nrk), kFixThreads, 0, stream>>>(p, pl.G, rows, fl);
+      nvae::launch(conv_tc_fixup_kernel<WGRAD>, dim3(fl.n, kBM / rows, nrk), kFixThreads, 0, stream, p, pl.G, rows, fl);
       NVAE_RETURN_IF_LAUNCH_FAILED();
     }
   }
@@ -1418,7 +1619,12 @@ int nvae_conv2d_fwd_tc(const NvaeConvDesc* d, const float* x, const float* x2, c
   if (d->Cin2 > 0) rc = make_map_nhwc(&maps.m[1], x2, d->N, d->H, d->W, d->Cin2, d->Cin2, pl.t.tw, pl.t.th, pl.t.tn);
   else maps.m[1] = maps.m[0];
   if (rc) return rc;
-  rc = make_map_2d(&maps.m[2], w_tr, d->Cout, (int64_t)taps * Ct, pl.pair ? pl.BN / 2 : pl.BN);
+  const float* bsrc = w_tr;
+  if (pl.f16) {
+    rc = f16_prepare(&p, pl, x, (int64_t)d->N * d->H * d->W * d->Cin, w_tr, (int64_t)d->Cout * taps * Ct, ws, stream, &bsrc);
+    if (rc) return rc;
+  }
+  rc = make_map_2d(&maps.m[2], bsrc, d->Cout, (int64_t)taps * Ct, pl.pair ? pl.BN / 2 : pl.BN);
   if (rc) return rc;
   return launch<false>(maps, p, pl, stream);
 }
@@ -1464,7 +1670,12 @@ int nvae_conv2d_dgrad_tc(const NvaeConvDesc* d, const float* dy, const float* w_
     int rc = make_map_nhwc(&maps.m[0], dy + d->y_off, d->N, d->Ho, d->Wo, d->Cout, ld, pl.t.tw, pl.t.th, pl.t.tn);
     if (rc) return rc;
     maps.m[1] = maps.m[0];
-    rc = make_map_2d(&maps.m[2], w_rnd, (int64_t)taps * Ct, d->Cout, pl.pair ? pl.BN / 2 : pl.BN);
+    const float* bsrc = w_rnd;
+    if (pl.f16) {
+      rc = f16_prepare(&p, pl, dy, (int64_t)d->N * d->Ho * d->Wo * d->Cout, w_rnd, (int64_t)taps * Ct * d->Cout, ws, stream, &bsrc);
+      if (rc) return rc;
+    }
+    rc = make_map_2d(&maps.m[2], bsrc, (int64_t)taps * Ct, d->Cout, pl.pair ? pl.BN / 2 : pl.BN);
     if (rc) return rc;
     rc = launch<false>(maps, p, pl, stream);
     if (rc) return rc;
@@ -1522,7 +1733,7 @@ int nvae_round_tf32_inplace(float* p, int64_t n, cudaStream_t stream) {
   if ((n & 3) || !aligned16(p)) return NVAE_E_BADSHAPE;
   int64_t g = ceil_div(n / 4, 256);
   if (g > kNumSMs * 16) g = kNumSMs * 16;
-  round_tf32_kernel<<<(int)g, 256, 0, stream>>>(p, n / 4);
+  nvae::launch(round_tf32_kernel, (int)g, 256, 0, stream, p, n / 4);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kDwThreads, 3) dwconv5x5_kernel(const float* _
                                                                   int W, int C, const float* __restrict__ wts,
                                                                   const float* __restrict__ bias, float* __restrict__ y,
                                                                   int imgs, int WQ, int PH, int PW) {
+  nvae::pdl_enter();
   extern __shared__ __align__(16) float smem[];
   float* tile = smem;
   const int c0 = blockIdx.x * kDwCC, n0 = blockIdx.y * imgs;
@@ -143,6 +144,7 @@ template <int WT>
 __global__ void __launch_bounds__(kDwThreads, 2) dwconv5x5_bwd_filter_kernel(
     const float* __restrict__ x, const float* __restrict__ stat, int act, const float* __restrict__ dy, int N, int H,
     int W, int C, float* __restrict__ partial, int imgs, int PH, int PW) {
+  nvae::pdl_enter();
   extern __shared__ __align__(16) float smem[];
   float* tile = smem;                                  // haloed activated input
   float* dtile = smem + (size_t)imgs * PH * PW * kDwCC;  // [imgs][H][W][32] dy; reused as the cross-warp buffer
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv5x5_bwd_filter_kernel(
 
 __global__ void dwconv5x5_bwd_filter_reduce_kernel(const float* __restrict__ partial, int ngroups, int C,
                                                    float* __restrict__ dw, float* __restrict__ dbias) {
+  nvae::pdl_enter();
   const int total = 26 * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -244,7 +247,7 @@ static int dw_launch(const float* x, const float* stat, int act, int N, int H, i
     NVAE_CUDA_TRY(cudaFuncSetAttribute(dwconv5x5_kernel<FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured[FLIP] = 200 * 1024;
   }
-  dwconv5x5_kernel<FLIP><<<dim3(g.nchunks, g.ngroups), kDwThreads, smem, stream>>>(x, stat, act, N, H, W, C, w, bias, y,
+  nvae::launch(dwconv5x5_kernel<FLIP>, dim3(g.nchunks, g.ngroups), kDwThreads, smem, stream, x, stat, act, N, H, W, C, w, bias, y,
                                                                                    g.imgs, g.WQ, g.PH, g.PW);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
@@ -293,7 +296,7 @@ extern "C" int nvae_dwconv5x5_bwd_filter(const float* x, const float* stat, int 
                                          200 * 1024));                                                                \
       configured = true;                                                                                              \
     }                                                                                                                 \
-    dwconv5x5_bwd_filter_kernel<WT_><<<grid, kDwThreads, smem, stream>>>(x, stat, act, dy, N, H, W, C, partial, g.imgs, \
+    nvae::launch(dwconv5x5_bwd_filter_kernel<WT_>, grid, kDwThreads, smem, stream, x, stat, act, dy, N, H, W, C, partial, g.imgs, \
                                                                          g.PH, g.PW);                                 \
   } while (0)
   if (W <= 4) NVAE_DW_FILTER(4);
@@ -302,7 +305,7 @@ extern "C" int nvae_dwconv5x5_bwd_filter(const float* x, const float* stat, int 
   else return NVAE_E_UNSUPPORTED;
 #undef NVAE_DW_FILTER
   NVAE_RETURN_IF_LAUNCH_FAILED();
-  dwconv5x5_bwd_filter_reduce_kernel<<<(26 * C + 255) / 256, 256, 0, stream>>>(partial, g.ngroups, C, dw, dbias);
+  nvae::launch(dwconv5x5_bwd_filter_reduce_kernel, (26 * C + 255) / 256, 256, 0, stream, partial, g.ngroups, C, dw, dbias);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kLatThreads) latent_fwd_kernel(const float* __
                                                                  float* __restrict__ z, float* __restrict__ kl,
                                                                  float* __restrict__ log_q, float* __restrict__ log_p,
                                                                  float* __restrict__ dist, int64_t dist_stride) {
+  nvae::pdl_enter();
   __shared__ float red[33];
   const int b = blockIdx.x, n = HW * L;
   const int64_t base = (int64_t)b * n;
@@ -84,6 +85,7 @@ __global__ void latent_bwd_kernel(const float* __restrict__ enc_p, const float* 
                                   const float* __restrict__ eps, const float* __restrict__ dz,
                                   const float* __restrict__ kl_weight, int64_t total, int L,
                                   float* __restrict__ d_enc_p, float* __restrict__ d_dec_p) {
+  nvae::pdl_enter();
   const float w = kl_weight[0];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / L;
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(256) loss_assemble_kernel(const float* __restr
                                                             int G, int B, float* __restrict__ kl_weight,
                                                             float* __restrict__ kl_loss,
                                                             float* __restrict__ scalars) {
+  nvae::pdl_enter();
   __shared__ float red[33];
   __shared__ float coeff[1024];
   const float beta = hyper[0];
@@ -168,6 +171,7 @@ __device__ __forceinline__ float softplusf(float l) { return fmaxf(l, 0.f) + log
 __global__ void __launch_bounds__(256) bernoulli_fwd_kernel(const float* __restrict__ logits,
                                                             const float* __restrict__ x, int H, int W, int C, int Cl,
                                                             int crop, float* __restrict__ recon) {
+  nvae::pdl_enter();
   __shared__ float red[33];
   const int b = blockIdx.x;
   const int Hc = H - 2 * crop, Wc = W - 2 * crop, n = Hc * Wc * C;
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(256) bernoulli_fwd_kernel(const float* __restr
 // dlogits = scale * (sigmoid(l) - x), summed over the broadcast channel when Cl==1
 __global__ void bernoulli_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ x, int64_t npix, int C,
                                      int Cl, float scale, float* __restrict__ dlogits) {
+  nvae::pdl_enter();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix * Cl; i += (int64_t)gridDim.x * blockDim.x) {
     const float l = logits[i];
     const float sg = 1.f / (1.f + expf(-l));
@@ -205,6 +210,7 @@ __global__ void __launch_bounds__(1024) bn_loss_kernel(const float* __restrict__
                                                        const int64_t* __restrict__ offsets,
                                                        const int32_t* __restrict__ sizes, int n, float lambda,
                                                        float* __restrict__ loss) {
+  nvae::pdl_enter();
   __shared__ float smax[1024];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k = warp; k < n; k += 32) {
@@ -241,7 +247,7 @@ extern "C" int nvae_latent_fwd(const float* enc_p, const float* dec_p, const flo
   if (B <= 0 || HW <= 0 || L <= 0) return NVAE_E_BADSHAPE;
   if (!enc_p || !eps || !z || !kl) return NVAE_E_NULLPTR;
   if ((log_q == nullptr) != (log_p == nullptr)) return NVAE_E_NULLPTR;
-  latent_fwd_kernel<<<B, kLatThreads, 0, stream>>>(enc_p, dec_p, eps, HW, L, z, kl, log_q, log_p, dist,
+  nvae::launch(latent_fwd_kernel, B, kLatThreads, 0, stream, enc_p, dec_p, eps, HW, L, z, kl, log_q, log_p, dist,
                                                    (int64_t)B * HW * L);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
@@ -256,7 +262,7 @@ extern "C" int nvae_latent_bwd(const float* enc_p, const float* dec_p, const flo
   const int64_t total = (int64_t)B * HW * L;
   int64_t grid = ceil_div(total, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  latent_bwd_kernel<<<(int)grid, 256, 0, stream>>>(enc_p, dec_p, eps, dz, kl_weight, total, L, d_enc_p, d_dec_p);
+  nvae::launch(latent_bwd_kernel, (int)grid, 256, 0, stream, enc_p, dec_p, eps, dz, kl_weight, total, L, d_enc_p, d_dec_p);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -266,7 +272,7 @@ extern "C" int nvae_loss_assemble(const float* kl_all, const float* recon, const
                                   float* scalars, nvae_stream_t stream) {
   if (G <= 0 || G > 1024 || B <= 0) return NVAE_E_BADSHAPE;
   if (!kl_all || !alphas || !hyper || !kl_loss) return NVAE_E_NULLPTR;
-  loss_assemble_kernel<<<1, 256, 0, stream>>>(kl_all, recon, bn_loss, alphas, hyper, balancing, G, B, kl_weight, kl_loss,
+  nvae::launch(loss_assemble_kernel, 1, 256, 0, stream, kl_all, recon, bn_loss, alphas, hyper, balancing, G, B, kl_weight, kl_loss,
                                               scalars);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
@@ -277,7 +283,7 @@ extern "C" int nvae_bernoulli_ll_fwd(const float* logits, const float* x, int B,
   if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (Cl != C && Cl != 1) || crop < 0 || 2 * crop >= H || 2 * crop >= W)
     return NVAE_E_BADSHAPE;
   if (!logits || !x || !recon) return NVAE_E_NULLPTR;
-  bernoulli_fwd_kernel<<<B, 256, 0, stream>>>(logits, x, H, W, C, Cl, crop, recon);
+  nvae::launch(bernoulli_fwd_kernel, B, 256, 0, stream, logits, x, H, W, C, Cl, crop, recon);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -289,7 +295,7 @@ extern "C" int nvae_bernoulli_ll_bwd(const float* logits, const float* x, int B,
   const int64_t npix = (int64_t)B * H * W;
   int64_t grid = ceil_div(npix * Cl, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  bernoulli_bwd_kernel<<<(int)grid, 256, 0, stream>>>(logits, x, npix, C, Cl, scale, dlogits);
+  nvae::launch(bernoulli_bwd_kernel, (int)grid, 256, 0, stream, logits, x, npix, C, Cl, scale, dlogits);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -298,7 +304,7 @@ extern "C" int nvae_bn_loss_fwd(const float* params, const int64_t* offsets, con
                                 float sr_lambda, float* loss, nvae_stream_t stream) {
   if (n <= 0 || n > 1024) return NVAE_E_BADSHAPE;
   if (!params || !offsets || !sizes || !loss) return NVAE_E_NULLPTR;
-  bn_loss_kernel<<<1, 1024, 0, stream>>>(params, nullptr, offsets, sizes, n, sr_lambda, loss);
+  nvae::launch(bn_loss_kernel, 1, 1024, 0, stream, params, nullptr, offsets, sizes, n, sr_lambda, loss);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -307,7 +313,7 @@ extern "C" int nvae_bn_loss_bwd(const float* params, float* grads, const int64_t
                                 float sr_lambda, nvae_stream_t stream) {
   if (n <= 0 || n > 1024) return NVAE_E_BADSHAPE;
   if (!params || !grads || !offsets || !sizes) return NVAE_E_NULLPTR;
-  bn_loss_kernel<<<1, 1024, 0, stream>>>(params, grads, offsets, sizes, n, sr_lambda, nullptr);
+  nvae::launch(bn_loss_kernel, 1, 1024, 0, stream, params, grads, offsets, sizes, n, sr_lambda, nullptr);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }

@@ -7,6 +7,7 @@ namespace nvae {
 // hyper layout: [0]=beta, [1]=lr_t (= lr/(1-b1^t)), [2]=lr, [3]=t (1-based), [4]=steps used for beta
 __global__ void schedule_kernel(int64_t* counters, float* hyper, float warmup_iters, float lr0, float decay_steps,
                                 float b1, int advance) {
+  nvae::pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const int64_t steps = counters[0], iters = counters[1];
   const float beta = warmup_iters > 0.f ? fminf((float)steps / warmup_iters, 1.f) : 1.f;
@@ -26,6 +27,7 @@ __global__ void schedule_kernel(int64_t* counters, float* hyper, float warmup_it
 __global__ void adamax_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                               float* __restrict__ v, int64_t n4, const float* __restrict__ hyper, float b1, float b2,
                               float eps, float gs) {
+  nvae::pdl_enter();
   const float lr_t = hyper[1];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pv = *reinterpret_cast<float4*>(p + i * 4), mv = *reinterpret_cast<float4*>(m + i * 4),
@@ -43,23 +45,28 @@ __global__ void adamax_kernel(float* __restrict__ p, const float* __restrict__ g
 }
 
 __global__ void fill_kernel(float* p, int64_t n, float v) {
+  nvae::pdl_enter();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 __global__ void axpby_kernel(const float* __restrict__ x, float a, float* __restrict__ y, float b, int64_t n) {
+  nvae::pdl_enter();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = b == 0.f ? a * x[i] : fmaf(a, x[i], b * y[i]);
 }
 __global__ void reparam_kernel(const float* __restrict__ mu, const float* __restrict__ sigma,
                                const float* __restrict__ eps, float sigma_scale, float* __restrict__ z, int64_t n) {
+  nvae::pdl_enter();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     z[i] = fmaf(eps[i], sigma[i] * sigma_scale, mu[i]);
 }
 __global__ void broadcast_rows_kernel(const float* __restrict__ src, int64_t row, int B, float* __restrict__ dst) {
+  nvae::pdl_enter();
   const int64_t n = row * B;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = src[i % row];
 }
 __global__ void reduce_rows_kernel(const float* __restrict__ src, int64_t row, int B, float* __restrict__ dst) {
+  nvae::pdl_enter();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < row; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int b = 0; b < B; ++b) s += src[(int64_t)b * row + i];
@@ -78,6 +85,7 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2])
 }
 __global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed,
                                      const int64_t* __restrict__ counters, uint64_t stream_id) {
+  nvae::pdl_enter();
   const uint64_t step = counters ? (uint64_t)counters[0] : 0ull;
   const int64_t n4 = (n + 3) / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -106,6 +114,7 @@ __global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_
 // mode 0: sigmoid(l) (Bernoulli.probs_parameter / mean);  mode 1: U < sigmoid(l) (Bernoulli.sample)
 __global__ void bernoulli_image_kernel(const float* __restrict__ logits, int64_t n, int mode, uint64_t seed,
                                        uint64_t stream_id, float* __restrict__ out) {
+  nvae::pdl_enter();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float p = 1.f / (1.f + expf(-logits[i]));
     if (mode == 0) {
@@ -138,7 +147,7 @@ extern "C" const char* nvae_build_info(void) { return "libnvae_b200 sm_100a (tcg
 extern "C" int nvae_schedule_step(int64_t* counters, float* hyper, float warmup_iters, float lr0, float decay_steps,
                                   float b1, int advance, nvae_stream_t stream) {
   if (!counters || !hyper) return NVAE_E_NULLPTR;
-  schedule_kernel<<<1, 32, 0, stream>>>(counters, hyper, warmup_iters, lr0, decay_steps, b1, advance);
+  nvae::launch(schedule_kernel, 1, 32, 0, stream, counters, hyper, warmup_iters, lr0, decay_steps, b1, advance);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -147,7 +156,7 @@ extern "C" int nvae_adamax(float* p, const float* g, float* m, float* v, int64_t
                            float b2, float eps, float grad_scale, nvae_stream_t stream) {
   if (n <= 0 || (n & 3)) return NVAE_E_BADSHAPE;
   if (!p || !g || !m || !v || !hyper) return NVAE_E_NULLPTR;
-  adamax_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(p, g, m, v, n / 4, hyper, b1, b2, eps, grad_scale);
+  nvae::launch(adamax_kernel, grid_for(n / 4, 256), 256, 0, stream, p, g, m, v, n / 4, hyper, b1, b2, eps, grad_scale);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -155,7 +164,7 @@ extern "C" int nvae_adamax(float* p, const float* g, float* m, float* v, int64_t
 extern "C" int nvae_fill(float* p, int64_t n, float value, nvae_stream_t stream) {
   if (n <= 0) return NVAE_E_BADSHAPE;
   if (!p) return NVAE_E_NULLPTR;
-  fill_kernel<<<grid_for(n, 256), 256, 0, stream>>>(p, n, value);
+  nvae::launch(fill_kernel, grid_for(n, 256), 256, 0, stream, p, n, value);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -163,7 +172,7 @@ extern "C" int nvae_fill(float* p, int64_t n, float value, nvae_stream_t stream)
 extern "C" int nvae_axpby(const float* x, float a, float* y, float b, int64_t n, nvae_stream_t stream) {
   if (n <= 0) return NVAE_E_BADSHAPE;
   if (!x || !y) return NVAE_E_NULLPTR;
-  axpby_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, a, y, b, n);
+  nvae::launch(axpby_kernel, grid_for(n, 256), 256, 0, stream, x, a, y, b, n);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -172,7 +181,7 @@ extern "C" int nvae_reparam(const float* mu, const float* sigma, const float* ep
                             int64_t n, nvae_stream_t stream) {
   if (n <= 0) return NVAE_E_BADSHAPE;
   if (!mu || !sigma || !eps || !z) return NVAE_E_NULLPTR;
-  reparam_kernel<<<grid_for(n, 256), 256, 0, stream>>>(mu, sigma, eps, sigma_scale, z, n);
+  nvae::launch(reparam_kernel, grid_for(n, 256), 256, 0, stream, mu, sigma, eps, sigma_scale, z, n);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -180,7 +189,7 @@ extern "C" int nvae_reparam(const float* mu, const float* sigma, const float* ep
 extern "C" int nvae_broadcast_rows(const float* src, int64_t row_elems, int B, float* dst, nvae_stream_t stream) {
   if (row_elems <= 0 || B <= 0) return NVAE_E_BADSHAPE;
   if (!src || !dst) return NVAE_E_NULLPTR;
-  broadcast_rows_kernel<<<grid_for(row_elems * B, 256), 256, 0, stream>>>(src, row_elems, B, dst);
+  nvae::launch(broadcast_rows_kernel, grid_for(row_elems * B, 256), 256, 0, stream, src, row_elems, B, dst);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -188,7 +197,7 @@ extern "C" int nvae_broadcast_rows(const float* src, int64_t row_elems, int B, f
 extern "C" int nvae_reduce_rows(const float* src, int64_t row_elems, int B, float* dst, nvae_stream_t stream) {
   if (row_elems <= 0 || B <= 0) return NVAE_E_BADSHAPE;
   if (!src || !dst) return NVAE_E_NULLPTR;
-  reduce_rows_kernel<<<grid_for(row_elems, 128), 128, 0, stream>>>(src, row_elems, B, dst);
+  nvae::launch(reduce_rows_kernel, grid_for(row_elems, 128), 128, 0, stream, src, row_elems, B, dst);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -197,7 +206,7 @@ extern "C" int nvae_philox_normal(float* out, int64_t n, uint64_t seed, const in
                                   nvae_stream_t stream) {
   if (n <= 0) return NVAE_E_BADSHAPE;
   if (!out) return NVAE_E_NULLPTR;
-  philox_normal_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, stream>>>(out, n, seed, counters, stream_id);
+  nvae::launch(philox_normal_kernel, grid_for((n + 3) / 4, 256), 256, 0, stream, out, n, seed, counters, stream_id);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -206,7 +215,7 @@ extern "C" int nvae_bernoulli_image(const float* logits, int64_t n, int mode, ui
                                     float* out, nvae_stream_t stream) {
   if (n <= 0 || (mode != 0 && mode != 1)) return NVAE_E_BADSHAPE;
   if (!logits || !out) return NVAE_E_NULLPTR;
-  bernoulli_image_kernel<<<grid_for(n, 256), 256, 0, stream>>>(logits, n, mode, seed, stream_id, out);
+  nvae::launch(bernoulli_image_kernel, grid_for(n, 256), 256, 0, stream, logits, n, mode, seed, stream_id, out);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }

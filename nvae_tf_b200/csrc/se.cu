@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(kSeThreads) se_pool_gate_kernel(
     const float* __restrict__ t, const float* __restrict__ stat, int HW, int C, int hid, const float* __restrict__ w1,
     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
     float* __restrict__ pooled, float* __restrict__ hidden, float* __restrict__ gate) {
+  nvae::pdl_enter();
   __shared__ float part[kSeThreads * 4];
   __shared__ float spool[kSeMaxC];
   __shared__ float shid[kSeMaxHid];
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(kSeThreads) se_pool_gate_kernel(
 __global__ void se_apply_kernel(const float* __restrict__ t, const float* __restrict__ stat,
                                 const float* __restrict__ xres, const float* __restrict__ gate, int64_t n4, int C4,
                                 int64_t hwc4, float alpha, float beta, float* __restrict__ y) {
+  nvae::pdl_enter();
   const int C = C4 * 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(kSeThreads) se_bwd_gate_kernel(
     const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ hidden,
     const float* __restrict__ gate, float beta, float* __restrict__ dz2, float* __restrict__ dh,
     float* __restrict__ dpool) {
+  nvae::pdl_enter();
   __shared__ float part[kSeThreads * 4];
   __shared__ float sdz[kSeMaxC];
   __shared__ float sdh[kSeMaxHid];
@@ -168,6 +171,7 @@ __global__ void se_bwd_weights_kernel(const float* __restrict__ pooled, const fl
                                       const float* __restrict__ dz2, const float* __restrict__ dh, int B, int C,
                                       int hid, float* __restrict__ dw1, float* __restrict__ db1,
                                       float* __restrict__ dw2, float* __restrict__ db2) {
+  nvae::pdl_enter();
   const int n1 = C * hid, total = 2 * n1 + C + hid;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     if (i < n1) {  // dw2[j][c]
@@ -191,6 +195,7 @@ __global__ void se_bwd_apply_kernel(const float* __restrict__ dy, const float* _
                                     const float* __restrict__ dpool, int64_t n4, int C4, int64_t hwc4, float inv_hw,
                                     float alpha, float beta, float* __restrict__ dt, float* __restrict__ dxres,
                                     int dxres_accumulate) {
+  nvae::pdl_enter();
   const int C = C4 * 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
@@ -233,10 +238,10 @@ extern "C" int nvae_se_fwd(const float* t, const float* stat, const float* xres,
   int rc = se_check(B, HW, C, hid);
   if (rc) return rc;
   if (!t || !xres || !w1 || !b1 || !w2 || !b2 || !pooled || !hidden || !gate || !y) return NVAE_E_NULLPTR;
-  se_pool_gate_kernel<<<B, kSeThreads, 0, stream>>>(t, stat, HW, C, hid, w1, b1, w2, b2, pooled, hidden, gate);
+  nvae::launch(se_pool_gate_kernel, B, kSeThreads, 0, stream, t, stat, HW, C, hid, w1, b1, w2, b2, pooled, hidden, gate);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   const int64_t n4 = (int64_t)B * HW * (C / 4);
-  se_apply_kernel<<<se_grid(n4, 256), 256, 0, stream>>>(t, stat, xres, gate, n4, C / 4, (int64_t)HW * (C / 4), alpha,
+  nvae::launch(se_apply_kernel, se_grid(n4, 256), 256, 0, stream, t, stat, xres, gate, n4, C / 4, (int64_t)HW * (C / 4), alpha,
                                                         beta, y);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
@@ -257,13 +262,13 @@ extern "C" int nvae_se_bwd(const float* dy, const float* t, const float* stat, i
   float* dz2 = reinterpret_cast<float*>(ws);
   float* dpool = dz2 + (size_t)B * C;
   float* dh = dpool + (size_t)B * C;
-  se_bwd_gate_kernel<<<B, kSeThreads, 0, stream>>>(dy, t, stat, HW, C, hid, w1, w2, hidden, gate, beta, dz2, dh, dpool);
+  nvae::launch(se_bwd_gate_kernel, B, kSeThreads, 0, stream, dy, t, stat, HW, C, hid, w1, w2, hidden, gate, beta, dz2, dh, dpool);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   const int total = 2 * C * hid + C + hid;
-  se_bwd_weights_kernel<<<(total + 127) / 128, 128, 0, stream>>>(pooled, hidden, dz2, dh, B, C, hid, dw1, db1, dw2, db2);
+  nvae::launch(se_bwd_weights_kernel, (total + 127) / 128, 128, 0, stream, pooled, hidden, dz2, dh, B, C, hid, dw1, db1, dw2, db2);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   const int64_t n4 = (int64_t)B * HW * (C / 4);
-  se_bwd_apply_kernel<<<se_grid(n4, 256), 256, 0, stream>>>(dy, gate, dpool, n4, C / 4, (int64_t)HW * (C / 4),
+  nvae::launch(se_bwd_apply_kernel, se_grid(n4, 256), 256, 0, stream, dy, gate, dpool, n4, C / 4, (int64_t)HW * (C / 4),
                                                             1.f / (float)HW, alpha, beta, dt, dxres, dxres_accumulate);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(kSnThreads) sn_wu_kernel(const float* __restri
                                                            const NvaeSnLayer* __restrict__ layers,
                                                            const int32_t* __restrict__ chunk_layer,
                                                            float* __restrict__ ws) {
+  nvae::pdl_enter();
   const NvaeSnLayer L = layers[chunk_layer[blockIdx.x]];
   const int chunk = blockIdx.x - L.chunk0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(kSnThreads) sn_vw_kernel(const float* __restri
                                                            const NvaeSnLayer* __restrict__ layers,
                                                            const int32_t* __restrict__ chunk_layer,
                                                            float* __restrict__ ws) {
+  nvae::pdl_enter();
   __shared__ float sv[kSnRows];
   const NvaeSnLayer L = layers[chunk_layer[blockIdx.x]];
   const int chunk = blockIdx.x - L.chunk0;
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(kSnThreads) sn_vw_kernel(const float* __restri
 __global__ void __launch_bounds__(kSnThreads) sn_finalize_kernel(float* __restrict__ state,
                                                                  const NvaeSnLayer* __restrict__ layers,
                                                                  float* __restrict__ ws, float* __restrict__ sigma) {
+  nvae::pdl_enter();
   __shared__ float red[33];
   const NvaeSnLayer L = layers[blockIdx.x];
   float nv2 = 0.f;
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(kSnThreads) sn_scale_pack_kernel(float* __rest
                                                                    const int32_t* __restrict__ chunk_layer,
                                                                    const float* __restrict__ sigma, int power_iter,
                                                                    int pack_exact) {
+  nvae::pdl_enter();
   constexpr int kTC = 64;  // columns per transposition tile
   __shared__ float tile[kSnRows][kTC + 1];
   const int li = chunk_layer[blockIdx.x];
@@ -174,15 +178,15 @@ extern "C" int nvae_spectral_norm(float* params, float* state, float* pack, cons
   if (pack_exact && pack == nullptr) return NVAE_E_NULLPTR;
   if (power_iter) {
     if (!state || !sigma_out || !ws) return NVAE_E_NULLPTR;
-    sn_wu_kernel<<<n_chunks_total, kSnThreads, 0, stream>>>(params, state, layers_dev, chunk_layer_dev, ws);
+    nvae::launch(sn_wu_kernel, n_chunks_total, kSnThreads, 0, stream, params, state, layers_dev, chunk_layer_dev, ws);
     NVAE_RETURN_IF_LAUNCH_FAILED();
-    sn_vw_kernel<<<n_chunks_total, kSnThreads, 0, stream>>>(params, layers_dev, chunk_layer_dev, ws);
+    nvae::launch(sn_vw_kernel, n_chunks_total, kSnThreads, 0, stream, params, layers_dev, chunk_layer_dev, ws);
     NVAE_RETURN_IF_LAUNCH_FAILED();
-    sn_finalize_kernel<<<n_layers, kSnThreads, 0, stream>>>(state, layers_dev, ws, sigma_out);
+    nvae::launch(sn_finalize_kernel, n_layers, kSnThreads, 0, stream, state, layers_dev, ws, sigma_out);
     NVAE_RETURN_IF_LAUNCH_FAILED();
   }
   if (power_iter || pack != nullptr) {
-    sn_scale_pack_kernel<<<n_chunks_total, kSnThreads, 0, stream>>>(params, pack, layers_dev, chunk_layer_dev,
+    nvae::launch(sn_scale_pack_kernel, n_chunks_total, kSnThreads, 0, stream, params, pack, layers_dev, chunk_layer_dev,
                                                                    sigma_out, power_iter, pack_exact);
     NVAE_RETURN_IF_LAUNCH_FAILED();
   }

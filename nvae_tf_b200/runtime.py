@@ -496,11 +496,18 @@ def _bn_backward(rt: Runtime, dout: torch.Tensor, x: DeviceTensor, stat: Optiona
 def bn_act(rt: Runtime, x: DeviceTensor, bn, act: int, training: bool, upsample: bool = False) -> DeviceTensor:
     """act(BN(x)) [-> nearest x2]; bn=None is a bare activation (layers.ELU / activations.swish)."""
     N, H, W, Cc = x.shape
-    stat = bn_stats(rt, x, bn, training) if bn is not None else None
     up = (H, W) if upsample else (0, 0)
     out = rt.empty(N, 2 * H, 2 * W, Cc) if upsample else rt.empty(N, H, W, Cc)
-    rt.lib.bn_act_fwd(x.ptr(), _rows(x.data), Cc, stat.data_ptr() if stat is not None else None, act, up[0], up[1],
-                      int(rt.precision == _lib.NVAE_PREC_TF32), out.data_ptr(), rt.stream)
+    rnd = int(rt.precision == _lib.NVAE_PREC_TF32)
+    if bn is not None:  # statistics + apply + activation: one launch when the tensor fits L2
+        stat = rt.empty(4, Cc)
+        ws, wsb = rt.workspace(rt.lib._nvae_bn_ws_bytes(_rows(x.data), Cc))
+        rt.lib.bn_fwd(x.ptr(), _rows(x.data), Cc, bn.gamma.ptr(), bn.beta.ptr(), bn.moving_mean.ptr(),
+                      bn.moving_variance.ptr(), int(training), bn.momentum, bn.epsilon, stat.data_ptr(), act, up[0],
+                      up[1], rnd, out.data_ptr(), ws, wsb, rt.stream)
+    else:
+        stat = None
+        rt.lib.bn_act_fwd(x.ptr(), _rows(x.data), Cc, None, act, up[0], up[1], rnd, out.data_ptr(), rt.stream)
     y = DeviceTensor(out, x.needs_grad or bn is not None)
     if rt.tape is not None:
         def bwd():

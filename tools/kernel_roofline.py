@@ -53,6 +53,19 @@ def timed(fn, reps=5, flush=True):
     return statistics.median(ts)
 
 
+def graph_timed(fn, iters=10):
+    """Device time of one fn() inside a CUDA graph (iters back-to-back calls per replay): no CPU launch overhead."""
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.graph(g, stream=s):
+        for _ in range(iters):
+            fn()
+    return timed(g.replay, reps=7, flush=False) / iters
+
+
 def row(name, shape, nbytes, us):
     gbs = nbytes / us / 1e3
     print(f"| `{name}` | {shape} | {nbytes / 1e6:.1f} | {us:.1f} | {gbs:.0f} | {100 * gbs / HBM:.0f}% |")
@@ -100,6 +113,26 @@ def membound():
                                                             dw.depthwise_kernel.gptr(), dw.bias.gptr(), ws, wsb, rt.stream))
                 row("dwconv5x5_bwd_filter", tag, 8 * n, us)
             del x, y, dy, dx
+        small_rows = []
+        for shp in [(144, 4, 4, 256), (144, 4, 4, 1536), (144, 8, 8, 128), (144, 8, 8, 768), (144, 16, 16, 64)]:
+            # the model's own L2-resident BN tensors: launch-/latency-bound, timed WITHOUT an L2 flush
+            N, H, W, Cc = shp
+            rows, n = N * H * W, N * H * W * Cc
+            x, dy = torch.randn(*shp, device="cuda"), torch.randn(*shp, device="cuda")
+            y, dx = torch.empty_like(x), torch.empty_like(x)
+            g, b, mm, mv = (torch.ones(Cc, device="cuda") for _ in range(4))
+            dg, db = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+            stat = torch.empty(4, Cc, device="cuda")
+            ws, wsb = rt.workspace(lib._nvae_bn_ws_bytes(rows, Cc))
+            def call(f):  # launch on the capturing stream
+                return lambda: f(torch.cuda.current_stream().cuda_stream)
+            uf = graph_timed(call(lambda st: lib.bn_fwd(x.data_ptr(), rows, Cc, g.data_ptr(), b.data_ptr(), mm.data_ptr(),
+                                                        mv.data_ptr(), 1, 0.05, 1e-5, stat.data_ptr(), 1, 0, 0, 0,
+                                                        y.data_ptr(), ws, wsb, st)))
+            ub = graph_timed(call(lambda st: lib.bn_act_bwd(dy.data_ptr(), x.data_ptr(), rows, Cc, stat.data_ptr(), 1, 0, 0,
+                                                            1, None, 0.0, 0, dx.data_ptr(), dg.data_ptr(), db.data_ptr(),
+                                                            ws, wsb, st)))
+            small_rows.append((f"[{N},{H},{W},{Cc}]", 4 * n / 1e6, uf, ub))
         for shp in [(256, 14, 14, 64), (256, 7, 7, 128), (144, 32, 32, 32)]:  # cell outputs: SE + residual merge
             N, H, W, Cc = shp
             if Cc not in ses:
@@ -145,6 +178,11 @@ def membound():
         us = timed(lambda: lib.adamax(pbuf.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, hyper.data_ptr(), 0.9,
                                       0.999, 1e-7, 1.0, rt.stream))
         row("adamax (whole parameter arena)", "[40.1M]", 28 * n, us)
+        fused = os.environ.get("NVAE_BN_FUSED", "1") != "0"
+        print(f"\n## BatchNorm at the model's own L2-resident shapes (inside a CUDA graph, no L2 flush; {'one cluster launch' if fused else 'split kernels, NVAE_BN_FUSED=0'})\n")
+        print("| tensor | MB | fwd: stats + apply + swish, us | bwd: reduce + dgamma/dbeta + dx, us |\n|---|---:|---:|---:|")
+        for tag, mb, uf, ub in small_rows:
+            print(f"| {tag} | {mb:.1f} | {uf:.1f} | {ub:.1f} |")
 
 
 def cells():
@@ -193,4 +231,5 @@ if __name__ == "__main__":
     torch.cuda.set_device(0)
     print("# Per-kernel roofline and residual-cell micro-benchmark (B200, measured by tools/kernel_roofline.py)\n")
     membound()
-    cells()
+    if "--no-cells" not in sys.argv:
+        cells()
