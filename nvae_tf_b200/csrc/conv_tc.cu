@@ -614,7 +614,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 else tma_load_4d(sa + (uint32_t)j * box_bytes, &maps.m[js[j]], full, jc[j], jw[j], h0 + jh[j], n0);
               }
             }
-            if (p.dy_chunked) {
+            if (p.f16) {
+              // packed dY [pixel][Cout/64][hi|lo][64 x fp16]: one box = the tile's BN/64 channel chunks, both parts
+              tma_load_5d(sa + p.a_bytes, &maps.m[4], full, 0, 0, h0, n0, nt * (nb >> 1) * 2);
+            } else if (p.dy_chunked) {
               tma_load_5d(sa + p.a_bytes, &maps.m[4], full, 0, 0, h0, n0, nt * nb);
             } else {
               for (int b = 0; b < nb; ++b)
@@ -639,8 +642,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // everything else in its loop is kept off the critical path: ring indices, barrier addresses and operand
         // descriptors advance incrementally (no divisions), and the 12 MMAs of a stage are issued back to back.
         constexpr uint64_t kAdv = WGRAD ? 64u : 2u;
-        const uint64_t b_desc0 = WGRAD ? umma_desc_sw128(stage_base + p.a_bytes, box_bytes, 512, 1)
-                                       : umma_desc_sw128(stage_base + p.a_bytes, 16, 1024);
+        // wgrad 3xFP16: B = packed dY, MN-major fp16, 128B swizzle: atom = 64 channels x 8 pixels (1 KB); the tile's
+        // chunks lie [c0 hi][c0 lo][c1 hi]... (4 KB each) -> LBO (next 64 channels) = 8 KB, SBO (next 8 pixels) = 1 KB
+        const uint64_t b_desc0 = (WGRAD && p.f16) ? umma_desc_sw128(stage_base + p.a_bytes, 8192, 1024, 2)
+                                 : WGRAD          ? umma_desc_sw128(stage_base + p.a_bytes, box_bytes, 512, 1)
+                                                  : umma_desc_sw128(stage_base + p.a_bytes, 16, 1024);
         const uint64_t lb_desc0 = WGRAD ? umma_desc_sw128(lo_base, box_bytes, 512, 1) : umma_desc_sw128(lo_base, 16, 1024);
         const uint64_t st_step = (uint64_t)(stage_bytes >> 4), lo_step = (uint64_t)(lo_bytes >> 4);
         const uint32_t a_base = tmem + (uint32_t)(p.acc_bufs * p.BN);
@@ -650,8 +656,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         uint32_t ph = 0, lph = 0, a_hi = a_base;
         uint64_t db = b_desc0, lb = lb_desc0;
         (void)it;
-        const bool f16 = !WGRAD && !PAIR && p.f16;
-        const uint32_t idesc_h = umma_idesc_f16(p.BN, 0);
+        const bool f16 = !PAIR && p.f16;
+        const uint32_t idesc_h = umma_idesc_f16(p.BN, WGRAD ? 1 : 0);
+        // K = 16 step / low-part offset of the B descriptor (16-byte units): forward/dgrad rows are
+        // [hi 2 x 32 B | lo 2 x 32 B]; wgrad steps 16 pixel rows of 128 B and finds the low parts 4 KB further
+        const uint64_t hk = WGRAD ? 128u : 2u, hlo = WGRAD ? 256u : 4u;
         const uint32_t a_slot = f16 ? 32u : 64u;  // TMEM columns per A ring slot
         for (int sp = 0; sp < so.n; ++sp)
         for (long long u = so.lo[sp], u_end = so.hi[sp]; u < u_end; ++seg) {
@@ -675,13 +684,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               // pre-split B row (TMA, raw ring): [hi k0..15 | hi k16..31 | lo k0..15 | lo k16..31], 32 bytes each
               TC_CYC(it, 8);
 #pragma unroll
-              for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + 2u * j, idesc_h, accum | (j > 0));
+              for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + hk * j, idesc_h, accum | (j > 0));
               TC_CYC(it, 9);
 #pragma unroll
-              for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + 4u + 2u * j, idesc_h, 1u);
+              for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + hlo + hk * j, idesc_h, 1u);
               TC_CYC(it, 10);
 #pragma unroll
-              for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_lo + 8u * j, db + 2u * j, idesc_h, 1u);
+              for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_lo + 8u * j, db + hk * j, idesc_h, 1u);
               TC_CYC(it, 11);
               umma_commit(loe0 + 8u * ls);
               TC_CYC(it, 2);
@@ -827,19 +836,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (gt == 0) TC_CYC(it, 5);
           const uint8_t* raw = smem_raw + (stage_base - smem_u32(smem_raw)) + (size_t)st * stage_bytes;
           float4* dst = reinterpret_cast<float4*>(smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)ls * lo_bytes);
-          if (!WGRAD && !PAIR && p.f16) {
+          if (!PAIR && p.f16) {
             // ---- 3xFP16: scale, split into fp16 high / low parts -> TMEM (16 + 16 packed columns); B arrives pre-split ----
             const uint32_t ta = tmem + (uint32_t)(p.acc_bufs * p.BN) + (uint32_t)ls * 32u + ((uint32_t)((warp & 3) * 32) << 16);
             {
-              const int m = (warp & 3) * 32 + lane;
-              const float4* arow = reinterpret_cast<const float4*>(raw + m * 128);
               uint32_t hi[16], lw[16];
+              if (!WGRAD) {
+                const int m = (warp & 3) * 32 + lane;
+                const float4* arow = reinterpret_cast<const float4*>(raw + m * 128);
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint4 h, l;
-                f16_split8(arow[(2 * c) ^ (m & 7)], arow[(2 * c + 1) ^ (m & 7)], f16_sa, h, l);
-                hi[4 * c] = h.x; hi[4 * c + 1] = h.y; hi[4 * c + 2] = h.z; hi[4 * c + 3] = h.w;
-                lw[4 * c] = l.x; lw[4 * c + 1] = l.y; lw[4 * c + 2] = l.z; lw[4 * c + 3] = l.w;
+                for (int c = 0; c < 4; ++c) {
+                  uint4 h, l;
+                  f16_split8(arow[(2 * c) ^ (m & 7)], arow[(2 * c + 1) ^ (m & 7)], f16_sa, h, l);
+                  hi[4 * c] = h.x; hi[4 * c + 1] = h.y; hi[4 * c + 2] = h.z; hi[4 * c + 3] = h.w;
+                  lw[4 * c] = l.x; lw[4 * c + 1] = l.y; lw[4 * c + 2] = l.z; lw[4 * c + 3] = l.w;
+                }
+              } else {
+                // A^T: lane = (job, channel), K = the 32 pixels of the job's box (32-byte-atom swizzle, as in 3xTF32)
+                const float* box = reinterpret_cast<const float*>(raw + (size_t)(warp & 3) * p.KP * 128);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                  const int k0 = 2 * c, k1 = 2 * c + 1;
+                  const float v0 = box[k0 * 32 + ((((lane >> 3) ^ (k0 & 3)) << 3) | (lane & 7))] * f16_sa;
+                  const float v1 = box[k1 * 32 + ((((lane >> 3) ^ (k1 & 3)) << 3) | (lane & 7))] * f16_sa;
+                  const __half2 hh = __floats2half2_rn(v0, v1);
+                  const float2 hf = __half22float2(hh);
+                  const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                  hi[c] = *reinterpret_cast<const uint32_t*>(&hh);
+                  lw[c] = *reinterpret_cast<const uint32_t*>(&ll);
+                }
               }
               tmem_st16(ta, hi);
               tmem_st16(ta + 16u, lw);
@@ -1167,6 +1192,23 @@ __global__ void __launch_bounds__(256) f16_pack_b_kernel(const float* __restrict
   }
 }
 
+// wgrad 3xFP16 B operand: dY [pixels][C] fp32 -> [pixels][C/64][hi|lo][64 x fp16] (same bytes), scaled by the
+// absmax slot 1.  One thread per 8 channels.
+__global__ void __launch_bounds__(256) f16_pack_dy_kernel(const float* __restrict__ dy, int64_t n8, int C8,
+                                                          const float* __restrict__ amax, uint4* __restrict__ out) {
+  nvae::pdl_enter();
+  const float s = f16_in_scale(__ldg(amax + 1));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / C8;
+    const int c8 = (int)(i - pix * C8);  // 8-channel group of the pixel; 8 groups per 64-channel chunk
+    uint4 h, l;
+    f16_split8(ldg4(dy + i * 8), ldg4(dy + i * 8 + 4), s, h, l);
+    uint4* o = out + pix * (int64_t)(2 * C8) + (c8 >> 3) * 16 + (c8 & 7);
+    o[0] = h;
+    o[8] = l;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1278,6 +1320,22 @@ int make_map_chunked(CUtensorMap* m, const float* base, int N, int H, int W, int
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NVAE_OK : NVAE_E_DRIVER;
+}
+
+// wgrad 3xFP16: 5-D view of the packed dY [N,H,W][C/64][hi|lo][64 x fp16] as {64 fp16, W, H, N, 2*C/64}; the box takes
+// the `nhalf` (= 2 * BN/64) 128-byte half-chunks of one N tile, which land [c0 hi][c0 lo][c1 hi]... of KP x 128 B each
+int make_map_packed_dy(CUtensorMap* m, const void* base, int N, int H, int W, int C, int tw, int th, int tn, int nhalf) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return NVAE_E_DRIVER;
+  const cuuint64_t row = (cuuint64_t)C * 4;  // bytes per pixel (hi + lo)
+  cuuint64_t dims[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)(2 * (C / 64))};
+  cuuint64_t strides[4] = {row, (cuuint64_t)W * row, (cuuint64_t)H * W * row, 128};
+  cuuint32_t box[5] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn, (cuuint32_t)nhalf};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? NVAE_OK : NVAE_E_DRIVER;
 }
@@ -1404,9 +1462,15 @@ bool pair_enabled() {
 // the operands for their absmax): taken by the large GEMMs, where the MMAs are what the time goes to.
 // NVAE_F16X3=0 disables it, NVAE_F16X3_MIN_GFLOP moves the threshold (tests set 0 to cover small shapes).
 bool use_f16x3(const NvaeConvDesc* d, int which) {
-  if (d->precision != NVAE_PREC_TF32X3 || which == 2 || d->stride != 1 || d->Cin2 != 0) return false;
+  if (d->precision != NVAE_PREC_TF32X3 || d->stride != 1 || d->Cin2 != 0) return false;
   if (d->y_off != 0 || (d->y_ld != 0 && d->y_ld != d->Cout)) return false;
-  if ((which == 0 ? d->Cin : d->Cout) % kChunk != 0) return false;  // whole 32-deep K chunks (the packed B rows)
+  if (which == 2) {  // packed dY: 64-channel chunks; x: whole 32-channel jobs
+    if (d->Cout % 64 != 0 || d->Cin % kChunk != 0) return false;
+    const char* w = getenv("NVAE_F16X3_WGRAD");
+    if (w != nullptr && w[0] == '0') return false;
+  } else if ((which == 0 ? d->Cin : d->Cout) % kChunk != 0) {
+    return false;  // whole 32-deep K chunks (the packed B rows)
+  }
   const char* e = getenv("NVAE_F16X3");
   if (e != nullptr && e[0] == '0') return false;
   const char* m = getenv("NVAE_F16X3_MIN_GFLOP");
@@ -1444,7 +1508,8 @@ bool plan_gemm(const NvaeConvDesc* d, int which, int ntaps, Plan* pl) {
 bool plan_wgrad(const NvaeConvDesc* d, Plan* pl) {
   if (!common_ok(d, 2)) return false;
   pl->pair = 0;
-  pl->f16 = 0;
+  pl->f16 = use_f16x3(d, 2);
+  pl->pack_bytes = 0;
   const int passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1;
   if (!pick_pix_tile(d->N, d->Ho, d->Wo, 32, 8, &pl->t) && !pick_pix_tile(d->N, d->Ho, d->Wo, 64, 8, &pl->t) &&
       !pick_pix_tile(d->N, d->Ho, d->Wo, 128, 8, &pl->t))
@@ -1461,7 +1526,14 @@ bool plan_wgrad(const NvaeConvDesc* d, Plan* pl) {
   pl->KU = pl->t.n_tiles;
   pl->a_bytes = 4u * KP * 128u;
   pl->b_bytes = (uint32_t)(pl->BN / kChunk) * KP * 128u;
-  return finish_plan(pl, passes, true);
+  // 3xFP16 needs the TMEM A path (32 pixels per stage) and N tiles made of whole 64-channel chunks
+  if (pl->f16 && (KP != 32 || pl->BN % 64 != 0 || d->Cout % pl->BN != 0)) pl->f16 = 0;
+  if (!finish_plan(pl, passes, true)) return false;
+  if (pl->f16) {
+    pl->pack_bytes = al256((size_t)d->N * d->Ho * d->Wo * d->Cout * sizeof(float)) + 256;
+    pl->part_bytes += pl->pack_bytes;
+  }
+  return true;
 }
 
 void fill_common(TcParams* p, const NvaeConvDesc* d, const Plan& pl, float* part) {
@@ -1723,6 +1795,24 @@ int nvae_conv2d_wgrad_tc(const NvaeConvDesc* d, const float* x, const float* x2,
   }
   if (p.dy_chunked) {
     rc = make_map_chunked(&maps.m[4], dy + d->y_off, d->N, d->Ho, d->Wo, d->Cout, ld, p.tw, p.th, p.tn, pl.BN / kChunk, swz);
+    if (rc) return rc;
+  }
+  if (pl.f16) {
+    // absmax(x), absmax(dY) -> scales; dY is split + re-laid out once (one extra pass over it), x by the converters
+    uint8_t* base = reinterpret_cast<uint8_t*>(ws) + pl.part_bytes - pl.pack_bytes;
+    unsigned* slot = reinterpret_cast<unsigned*>(base + pl.pack_bytes - 256);
+    cudaError_t e = cudaMemsetAsync(slot, 0, 2 * sizeof(unsigned), stream);
+    if (e != cudaSuccess) return (int)e;
+    auto blocks = [](int64_t n, int per) { int64_t g = ceil_div(n, per); return (int)(g < 1 ? 1 : (g > 4 * kNumSMs ? 4 * kNumSMs : g)); };
+    const int64_t nx = (int64_t)d->N * d->H * d->W * d->Cin, ndy = (int64_t)d->N * d->Ho * d->Wo * d->Cout;
+    const int g0 = blocks(nx / 4, 256 * 8), g1 = blocks(ndy / 4, 256 * 8);
+    nvae::launch(absmax2_kernel, g0 + g1, 256, 0, stream, x, nx / 4, dy, ndy / 4, g0, slot);
+    NVAE_RETURN_IF_LAUNCH_FAILED();
+    nvae::launch(f16_pack_dy_kernel, blocks(ndy / 8, 256 * 2), 256, 0, stream, dy, ndy / 8, d->Cout / 8,
+                 reinterpret_cast<const float*>(slot), reinterpret_cast<uint4*>(base));
+    NVAE_RETURN_IF_LAUNCH_FAILED();
+    p.amax = reinterpret_cast<const float*>(slot);
+    rc = make_map_packed_dy(&maps.m[4], base, d->N, d->Ho, d->Wo, d->Cout, p.tw, p.th, p.tn, 2 * (pl.BN / 64));
     if (rc) return rc;
   }
   return launch<true>(maps, p, pl, stream);
