@@ -304,6 +304,8 @@ struct TcParams {
                                 // as hi*hi + hi*lo + lo*hi with kind::f16 -- the same 22 significant bits per operand
                                 // as 3xTF32 at twice the tensor-pipe rate; the epilogue undoes the scales
   const float* amax;            // device: {absmax(A operand), absmax(B operand)}, written just before the launch
+  int nsub;                     // 3xFP16: the BN-wide tile is nsub accumulators of BN/nsub columns (one MMA each) that share
+                                // every staged + converted A tile -- fewer L2 -> shared-memory bytes per MAC
   int n_ntiles;                 // tile t = mt * n_ntiles + nt
   int KU;                       // k-units (pipeline stages) per tile
   int T;                        // tiles
@@ -569,6 +571,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             // PAIR: this CTA's half of the B tile (p.b_bytes covers BN/2 rows)
             tma_load_2d(sa + p.a_bytes, &maps.m[2], full, wt * p.bk_tap + kk,
                         wt * p.br_tap + nt * p.BN + (PAIR ? (int)crank * (p.BN >> 1) : 0));
+            if (!PAIR && p.nsub == 2)  // second sub-tile (a TMA box has at most 256 rows)
+              tma_load_2d(sa + p.a_bytes + (p.b_bytes >> 1), &maps.m[2], full, wt * p.bk_tap + kk,
+                          wt * p.br_tap + nt * p.BN + (p.BN >> 1));
             if (++c == nch) { c = 0; ++tap; }
           }
         } else {
@@ -657,7 +662,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         uint64_t db = b_desc0, lb = lb_desc0;
         (void)it;
         const bool f16 = !PAIR && p.f16;
-        const uint32_t idesc_h = umma_idesc_f16(p.BN, WGRAD ? 1 : 0);
+        const int bns = p.nsub == 2 ? p.BN >> 1 : p.BN;  // columns per MMA / accumulator
+        const uint32_t idesc_h = umma_idesc_f16(bns, WGRAD ? 1 : 0);
+        const uint64_t sub_step = (uint64_t)(p.b_bytes >> 5);  // second sub-tile's B: half the stage's B bytes, in 16-byte units
         // K = 16 step / low-part offset of the B descriptor (16-byte units): forward/dgrad rows are
         // [hi 2 x 32 B | lo 2 x 32 B]; wgrad steps 16 pixel rows of 128 B and finds the low parts 4 KB further
         const uint64_t hk = WGRAD ? 128u : 2u, hlo = WGRAD ? 256u : 4u;
@@ -691,6 +698,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               TC_CYC(it, 10);
 #pragma unroll
               for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_lo + 8u * j, db + hk * j, idesc_h, 1u);
+              if (p.nsub == 2) {  // same A slot against the second B sub-tile, into the second accumulator
+                const uint32_t acc2 = acc + (uint32_t)bns;
+                const uint64_t db2 = db + sub_step;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, a_hi + 8u * j, db2 + hk * j, idesc_h, accum | (j > 0));
+#pragma unroll
+                for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, a_hi + 8u * j, db2 + hlo + hk * j, idesc_h, 1u);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, a_lo + 8u * j, db2 + hk * j, idesc_h, 1u);
+              }
               TC_CYC(it, 11);
               umma_commit(loe0 + 8u * ls);
               TC_CYC(it, 2);
@@ -1376,7 +1393,7 @@ bool common_ok(const NvaeConvDesc* d, int which) {
 // Launch plan shared by the three directions: tiles, stages, stream-K grid, partial-buffer size.
 struct Plan {
   PixTile t;
-  int BN, stages, lo_stages, a_tmem, acc_bufs, pair, n_mtiles, n_ntiles, KU, G, njobs, f16;
+  int BN, stages, lo_stages, a_tmem, acc_bufs, pair, n_mtiles, n_ntiles, KU, G, njobs, f16, nsub;
   size_t pack_bytes;   // 3xFP16: the split B operand (same bytes as the fp32 weights) + 256 for the absmax slots, behind the partials
   uint32_t a_bytes, b_bytes;
   long long U;
@@ -1431,6 +1448,12 @@ bool finish_plan(Plan* pl, int passes, bool wgrad) {
         while (deep > 2 && budget < deep * lo_slot + 3 * raw) --deep;
         if (deep > 2) { pl->acc_bufs = 1; pl->lo_stages = deep; }
       }
+    }
+    if (pl->nsub == 2) {  // two accumulators side by side fill TMEM up to the A ring: no accumulator double buffer
+      pl->acc_bufs = 1;
+      pl->lo_stages = (512 - pl->BN) / 32;
+      if (pl->lo_stages > 6) pl->lo_stages = 6;
+      if (pl->lo_stages < 2) return false;
     }
     if (budget < pl->lo_stages * lo_slot + 2 * raw) return false;
     pl->stages = (int)((budget - pl->lo_stages * lo_slot) / raw);
@@ -1490,6 +1513,14 @@ bool plan_gemm(const NvaeConvDesc* d, int which, int ntaps, Plan* pl) {
   // 3xTF32 forward / dgrad run as 2-CTA pairs (N tile a multiple of 32: cta_group::2 MMA granularity)
   pl->pair = passes == 3 && pl->n_mtiles >= 2 && pair_enabled();
   pl->BN = pick_bn(n_total, pl->pair ? 32 : 16, passes == 3 ? 192 : 256);
+  pl->nsub = 1;
+  {  // 3xFP16, 192 < N <= 384: one tile of two accumulators sharing the A tiles (NVAE_F16X3_NSUB=0 disables)
+    const char* e = getenv("NVAE_F16X3_NSUB");
+    if (pl->f16 && n_total > 192 && n_total <= 384 && n_total % 32 == 0 && !(e != nullptr && e[0] == '0')) {
+      pl->BN = n_total;
+      pl->nsub = 2;
+    }
+  }
   pl->n_ntiles = (int)ceil_div(n_total, pl->BN);
   const int nch = which == 0 ? (int)(ceil_div(d->Cin, kChunk) + ceil_div(d->Cin2, kChunk)) : (int)ceil_div(d->Cout, kChunk);
   pl->KU = ntaps * nch;
@@ -1519,9 +1550,17 @@ bool plan_wgrad(const NvaeConvDesc* d, Plan* pl) {
   pl->njobs = d->R * d->S * nch;
   pl->n_mtiles = (pl->njobs + 3) / 4;
   pl->BN = pick_bn(d->Cout, 32, passes == 3 ? 192 : 256);
+  pl->nsub = 1;
+  {
+    const char* e = getenv("NVAE_F16X3_NSUB");
+    if (pl->f16 && KP == 32 && d->Cout > 192 && d->Cout <= 384 && d->Cout % 128 == 0 && !(e != nullptr && e[0] == '0')) {
+      pl->BN = d->Cout;
+      pl->nsub = 2;
+    }
+  }
   // at least 2 raw + 2 lo (3xTF32) / 3 raw (TF32) slots in shared memory
   const size_t want = passes == 3 ? 4 : 3;
-  while ((size_t)(4 + pl->BN / kChunk) * KP * 128 * want > (size_t)kSmemBudget - 2048 && pl->BN > 32) pl->BN -= 32;
+  while (pl->nsub == 1 && (size_t)(4 + pl->BN / kChunk) * KP * 128 * want > (size_t)kSmemBudget - 2048 && pl->BN > 32) pl->BN -= 32;
   pl->n_ntiles = (int)ceil_div(d->Cout, pl->BN);
   pl->KU = pl->t.n_tiles;
   pl->a_bytes = 4u * KP * 128u;
@@ -1541,7 +1580,7 @@ void fill_common(TcParams* p, const NvaeConvDesc* d, const Plan& pl, float* part
   p->oH = d->Ho; p->oW = d->Wo; p->os = 1; p->ooh = 0; p->oow = 0;
   p->a5d = 0; p->par_c = d->Cin;
   p->tw = pl.t.tw; p->th = pl.t.th; p->tn = pl.t.tn; p->tiles_h = pl.t.tiles_h;
-  p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->acc_bufs = pl.acc_bufs; p->pair = pl.pair; p->n_mtiles = pl.n_mtiles; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1; p->f16 = pl.f16; p->amax = nullptr;
+  p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->acc_bufs = pl.acc_bufs; p->pair = pl.pair; p->n_mtiles = pl.n_mtiles; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1; p->f16 = pl.f16; p->amax = nullptr; p->nsub = pl.nsub;
   p->n_ntiles = pl.n_ntiles; p->KU = pl.KU; p->U = pl.U;
   p->T = (pl.pair ? (pl.n_mtiles + 1) / 2 : pl.n_mtiles) * pl.n_ntiles; p->whole_tiles = pl.whole_tiles;
   p->a_bytes = pl.a_bytes; p->b_bytes = pl.b_bytes;
@@ -1696,7 +1735,7 @@ int nvae_conv2d_fwd_tc(const NvaeConvDesc* d, const float* x, const float* x2, c
     rc = f16_prepare(&p, pl, x, (int64_t)d->N * d->H * d->W * d->Cin, w_tr, (int64_t)d->Cout * taps * Ct, ws, stream, &bsrc);
     if (rc) return rc;
   }
-  rc = make_map_2d(&maps.m[2], bsrc, d->Cout, (int64_t)taps * Ct, pl.pair ? pl.BN / 2 : pl.BN);
+  rc = make_map_2d(&maps.m[2], bsrc, d->Cout, (int64_t)taps * Ct, (pl.pair || pl.nsub == 2) ? pl.BN / 2 : pl.BN);
   if (rc) return rc;
   return launch<false>(maps, p, pl, stream);
 }
@@ -1747,7 +1786,7 @@ int nvae_conv2d_dgrad_tc(const NvaeConvDesc* d, const float* dy, const float* w_
       rc = f16_prepare(&p, pl, dy, (int64_t)d->N * d->Ho * d->Wo * d->Cout, w_rnd, (int64_t)taps * Ct * d->Cout, ws, stream, &bsrc);
       if (rc) return rc;
     }
-    rc = make_map_2d(&maps.m[2], bsrc, (int64_t)taps * Ct, d->Cout, pl.pair ? pl.BN / 2 : pl.BN);
+    rc = make_map_2d(&maps.m[2], bsrc, (int64_t)taps * Ct, d->Cout, (pl.pair || pl.nsub == 2) ? pl.BN / 2 : pl.BN);
     if (rc) return rc;
     rc = launch<false>(maps, p, pl, stream);
     if (rc) return rc;
