@@ -276,6 +276,8 @@ __device__ __forceinline__ uint32_t tmem_alloc_cols(int bn, int passes) {
 __device__ __forceinline__ uint32_t tmem_acc_stride(int bn, int passes) {
   return passes == 3 ? (uint32_t)bn : tmem_cols_for(bn);
 }
+// first TMEM column of the A ring: behind the accumulator(s)
+__device__ __forceinline__ uint32_t tmem_a_ring(int bn, int acc_bufs, int dual) { return (uint32_t)((dual ? 2 : acc_bufs) * bn); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -304,6 +306,9 @@ struct TcParams {
                                 // as hi*hi + hi*lo + lo*hi with kind::f16 -- the same 22 significant bits per operand
                                 // as 3xTF32 at twice the tensor-pipe rate; the epilogue undoes the scales
   const float* amax;            // device: {absmax(A operand), absmax(B operand)}, written just before the launch
+  int dual;                     // 3xFP16: a CTA tile is TWO 128-row M tiles (mt = 2*(t / n_ntiles) + g) that share every
+                                // staged B tile: stage = [A0][A1][B], converter group g splits A_g, accumulator g at column
+                                // g*BN.  Partials / fix-up use the pair layout (p.pair = 1): [cta][slot][g][128][BN]
   int nsub;                     // 3xFP16: the BN-wide tile is nsub accumulators of BN/nsub columns (one MMA each) that share
                                 // every staged + converted A tile -- fewer L2 -> shared-memory bytes per MAC
   int n_ntiles;                 // tile t = mt * n_ntiles + nt
@@ -508,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int i = 0; i < p.lo_stages; ++i) {
       // a_tmem: one 4-warp converter group per stage (PAIR: of both CTAs); else all 8 converter warps
-      mbar_init(smem_u32(&ctl->conv[i]), (PAIR ? 2 : 1) * (p.a_tmem ? kConvThreads / 64 : kConvThreads / 32));
+      mbar_init(smem_u32(&ctl->conv[i]), (PAIR ? 2 : 1) * ((p.a_tmem && !p.dual) ? kConvThreads / 64 : kConvThreads / 32));
       mbar_init(smem_u32(&ctl->lo_empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -540,12 +545,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (long long u = so.lo[ph], u_end = so.hi[ph]; u < u_end;) {
         const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
         const int kb = (int)min((long long)p.KU, ka + (u_end - u));
-        const int mt = PAIR ? 2 * (t / p.n_ntiles) + (int)crank : t / p.n_ntiles, nt = t - (t / p.n_ntiles) * p.n_ntiles;
+        const bool dual = !PAIR && p.dual;
+        const int mt = PAIR ? 2 * (t / p.n_ntiles) + (int)crank : dual ? 2 * (t / p.n_ntiles) : t / p.n_ntiles,
+                  nt = t - (t / p.n_ntiles) * p.n_ntiles;
         if (!WGRAD) {
           int n0, h0;
           if (p.tn > 1) { n0 = mt * p.tn; h0 = 0; }
           else { n0 = mt / p.tiles_h; h0 = (mt - n0 * p.tiles_h) * p.th; }
-          const uint32_t tx = (uint32_t)(p.tw * p.th * p.tn) * 128u + p.b_bytes;
+          int n1 = 0, h1 = 0;  // dual: the second M tile (beyond the problem: TMA zero fill)
+          if (dual) {
+            if (p.tn > 1) { n1 = (mt + 1) * p.tn; h1 = 0; }
+            else { n1 = (mt + 1) / p.tiles_h; h1 = (mt + 1 - n1 * p.tiles_h) * p.th; }
+          }
+          const uint32_t a_tile = (uint32_t)(p.tw * p.th * p.tn) * 128u;
+          const uint32_t tx = (dual ? 2u : 1u) * a_tile + p.b_bytes;
           int tap = ka / nch, c = ka - tap * nch;
           for (int k = ka; k < kb; ++k, ++it) {
             const int ah = h0 + p.tap_dh[tap], aw = p.tap_dw[tap], wt = p.tap_w[tap];
@@ -563,6 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               kk = c * kChunk;
             } else if (c < p.nchunk1) {
               tma_load_4d(sa, &maps.m[0], full, c * kChunk, aw, ah, n0);
+              if (dual) tma_load_4d(sa + (p.a_bytes >> 1), &maps.m[0], full, c * kChunk, aw, h1 + p.tap_dh[tap], n1);
               kk = c * kChunk;
             } else {
               tma_load_4d(sa, &maps.m[1], full, (c - p.nchunk1) * kChunk, aw, ah, n0);
@@ -579,10 +593,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         } else {
           const uint32_t box_bytes = (uint32_t)p.KP * 128u;
           const int nb = p.BN / kChunk;
+          const int jmax = dual ? 8 : 4;
           int njob = p.njobs - mt * 4;
-          njob = njob > 4 ? 4 : njob;
-          int jc[4], jh[4], jw[4], js[4], jp[4];
-          for (int j = 0; j < 4; ++j) {
+          njob = njob > jmax ? jmax : njob;
+          int jc[8], jh[8], jw[8], js[8], jp[8];
+          for (int j = 0; j < jmax; ++j) {
             const int job = mt * 4 + j;
             const int tap = job / nch, c = job - tap * nch;
             const int r = tap / p.S, s = tap - r * p.S;
@@ -598,7 +613,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           const uint32_t tx = (uint32_t)(njob + nb) * box_bytes;
           // the tile's four jobs are consecutive channel chunks of ONE tap -> a single chunked box fetches them
-          const bool x_one = p.x_chunked && njob == 4 && (mt * 4) / nch == (mt * 4 + 3) / nch;
+          const bool x_one = p.x_chunked && njob >= 4 && (mt * 4) / nch == (mt * 4 + 3) / nch;
+          const bool x_one2 = dual && p.x_chunked && njob == 8 && (mt * 4 + 4) / nch == (mt * 4 + 7) / nch;
           for (int k = ka; k < kb; ++k, ++it) {
             int n0, h0;
             if (p.tn > 1) { n0 = k * p.tn; h0 = 0; }
@@ -614,10 +630,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (x_one) {
               tma_load_5d(sa, &maps.m[3], full, 0, jw[0], h0 + jh[0], n0, jc[0] / kChunk);
             } else {
-              for (int j = 0; j < njob; ++j) {
+              for (int j = 0; j < (njob < 4 ? njob : 4); ++j) {
                 if (p.a5d) tma_load_5d(sa + (uint32_t)j * box_bytes, &maps.m[0], full, jc[j], jw[j], jp[j], h0 + jh[j], n0);
                 else tma_load_4d(sa + (uint32_t)j * box_bytes, &maps.m[js[j]], full, jc[j], jw[j], h0 + jh[j], n0);
               }
+            }
+            if (x_one2) {
+              tma_load_5d(sa + 4u * box_bytes, &maps.m[3], full, 0, jw[4], h0 + jh[4], n0, jc[4] / kChunk);
+            } else {
+              for (int j = 4; j < njob; ++j)
+                tma_load_4d(sa + (uint32_t)j * box_bytes, &maps.m[js[j]], full, jc[j], jw[j], h0 + jh[j], n0);
             }
             if (p.f16) {
               // packed dY [pixel][Cout/64][hi|lo][64 x fp16]: one box = the tile's BN/64 channel chunks, both parts
@@ -654,7 +676,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                                   : umma_desc_sw128(stage_base + p.a_bytes, 16, 1024);
         const uint64_t lb_desc0 = WGRAD ? umma_desc_sw128(lo_base, box_bytes, 512, 1) : umma_desc_sw128(lo_base, 16, 1024);
         const uint64_t st_step = (uint64_t)(stage_bytes >> 4), lo_step = (uint64_t)(lo_bytes >> 4);
-        const uint32_t a_base = tmem + (uint32_t)(p.acc_bufs * p.BN);
+        const uint32_t a_base = tmem + tmem_a_ring(p.BN, p.acc_bufs, !PAIR && p.dual);
         const uint32_t full0 = smem_u32(&ctl->full[0]), empty0 = smem_u32(&ctl->empty[0]);
         const uint32_t conv0 = smem_u32(&ctl->conv[0]), loe0 = smem_u32(&ctl->lo_empty[0]);
         int st = 0, ls = 0, seg = 0, it = 0;
@@ -668,7 +690,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // K = 16 step / low-part offset of the B descriptor (16-byte units): forward/dgrad rows are
         // [hi 2 x 32 B | lo 2 x 32 B]; wgrad steps 16 pixel rows of 128 B and finds the low parts 4 KB further
         const uint64_t hk = WGRAD ? 128u : 2u, hlo = WGRAD ? 256u : 4u;
-        const uint32_t a_slot = f16 ? 32u : 64u;  // TMEM columns per A ring slot
+        const uint32_t a_slot = (f16 && !p.dual) ? 32u : 64u;  // TMEM columns per A ring slot (dual: two tiles x 32)
         for (int sp = 0; sp < so.n; ++sp)
         for (long long u = so.lo[sp], u_end = so.hi[sp]; u < u_end; ++seg) {
           const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
@@ -698,6 +720,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               TC_CYC(it, 10);
 #pragma unroll
               for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_lo + 8u * j, db + hk * j, idesc_h, 1u);
+              if (p.dual) {  // the second M tile's A (slot columns 32..63) against the same B, into the second accumulator
+                const uint32_t acc2 = acc + (uint32_t)p.BN, b_hi = a_hi + 32u, b_lo = a_hi + 48u;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, b_hi + 8u * j, db + hk * j, idesc_h, accum | (j > 0));
+#pragma unroll
+                for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, b_hi + 8u * j, db + hlo + hk * j, idesc_h, 1u);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, b_lo + 8u * j, db + hk * j, idesc_h, 1u);
+              }
               if (p.nsub == 2) {  // same A slot against the second B sub-tile, into the second accumulator
                 const uint32_t acc2 = acc + (uint32_t)bns;
                 const uint64_t db2 = db + sub_step;
@@ -842,20 +873,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int grp = (warp - 2) >> 2, gt = ((warp - 2) & 3) * 32 + lane;  // group, thread within the group (0..127)
         constexpr int kGT = kConvThreads / 2;
         const int n16b = (int)(p.b_bytes >> 4);
-        int st = grp % p.stages, ls = grp % p.lo_stages;
-        uint32_t ph = (uint32_t)(grp / p.stages) & 1u, lph = (uint32_t)(grp / p.lo_stages) & 1u;
+        const bool dual = !PAIR && p.dual;  // both groups work on EVERY stage: group g splits M tile g
+        const int it0 = dual ? 0 : grp, itstep = dual ? 1 : 2;
+        int st = it0 % p.stages, ls = it0 % p.lo_stages;
+        uint32_t ph = (uint32_t)(it0 / p.stages) & 1u, lph = (uint32_t)(it0 / p.lo_stages) & 1u;
         const float f16_sa = p.f16 ? f16_in_scale(__ldg(p.amax)) : 1.f;
-        for (int it = grp; it < n_units; it += 2) {
+        for (int it = it0; it < n_units; it += itstep) {
           if (gt == 0) TC_CYC(it, 3);
           mbar_wait(smem_u32(&ctl->lo_empty[ls]), lph ^ 1u);
           if (gt == 0) TC_CYC(it, 4);
           mbar_wait(smem_u32(&ctl->full[st]), ph);
           if (gt == 0) TC_CYC(it, 5);
-          const uint8_t* raw = smem_raw + (stage_base - smem_u32(smem_raw)) + (size_t)st * stage_bytes;
+          const uint8_t* raw = smem_raw + (stage_base - smem_u32(smem_raw)) + (size_t)st * stage_bytes +
+                               (dual ? (size_t)grp * (p.a_bytes >> 1) : 0);
           float4* dst = reinterpret_cast<float4*>(smem_raw + (lo_base - smem_u32(smem_raw)) + (size_t)ls * lo_bytes);
           if (!PAIR && p.f16) {
             // ---- 3xFP16: scale, split into fp16 high / low parts -> TMEM (16 + 16 packed columns); B arrives pre-split ----
-            const uint32_t ta = tmem + (uint32_t)(p.acc_bufs * p.BN) + (uint32_t)ls * 32u + ((uint32_t)((warp & 3) * 32) << 16);
+            const uint32_t ta = tmem + tmem_a_ring(p.BN, p.acc_bufs, dual) + (uint32_t)ls * (dual ? 64u : 32u) +
+                                (dual ? (uint32_t)grp * 32u : 0u) + ((uint32_t)((warp & 3) * 32) << 16);
             {
               uint32_t hi[16], lw[16];
               if (!WGRAD) {
@@ -891,8 +926,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&ctl->conv[ls]));
-            st += 2; if (st >= p.stages) { st -= p.stages; ph ^= 1u; }
-            ls += 2; if (ls >= p.lo_stages) { ls -= p.lo_stages; lph ^= 1u; }
+            st += itstep; if (st >= p.stages) { st -= p.stages; ph ^= 1u; }
+            ls += itstep; if (ls >= p.lo_stages) { ls -= p.lo_stages; lph ^= 1u; }
             continue;
           }
           const uint32_t ta = tmem + (uint32_t)(p.acc_bufs * p.BN) + (uint32_t)ls * 64u + ((uint32_t)((warp & 3) * 32) << 16);
@@ -990,20 +1025,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (long long u = so.lo[ph], u_end = so.hi[ph]; u < u_end; ++seg) {
       const int t = (int)(u / p.KU), ka = (int)(u - (long long)t * p.KU);
       const int kb = (int)min((long long)p.KU, ka + (u_end - u));
-      const int mt = PAIR ? 2 * (t / p.n_ntiles) + (int)crank : t / p.n_ntiles, nt = t - (t / p.n_ntiles) * p.n_ntiles;
+      const bool dual = !PAIR && p.dual;
+      const int nt = t - (t / p.n_ntiles) * p.n_ntiles;
       const bool full_tile = ka == 0 && kb == p.KU;
+      const int ab = seg % p.acc_bufs;
+      mbar_wait(smem_u32(&ctl->acc_full[ab]), ((uint32_t)(seg / p.acc_bufs)) & 1u);
+      tc_fence_after();
+      if (threadIdx.x == kThreads - 1) TC_STAMP(4);
+      for (int g = 0; g < (dual ? 2 : 1); ++g) {  // dual: accumulator g = M tile 2*(t / n_ntiles) + g
+      const int mt = PAIR ? 2 * (t / p.n_ntiles) + (int)crank : dual ? 2 * (t / p.n_ntiles) + g : t / p.n_ntiles;
+      const int hrank = PAIR ? (int)crank : g;
       {
         const RowCtx rc = row_ctx<WGRAD>(p, mt, row);
         epi->rowbase[row] = (rc.ok || !full_tile) ? rc.base : -1;
       }
       // slot 0: continues a tile begun by an earlier CTA; slot 1: begins a tile a later CTA finishes
-      // (PAIR: [pair][slot][rank][128][BN])
-      float* pdst = p.part + ((((int64_t)cta * 2 + (ka > 0 ? 0 : 1)) * (PAIR ? 2 : 1) + (PAIR ? crank : 0)) * kBM + lg * 32) * p.BN;
-      const int ab = seg % p.acc_bufs;
-      const uint32_t acc = tmem + (uint32_t)ab * tmem_acc_stride(p.BN, p.passes) + ((uint32_t)(lg * 32) << 16);
-      mbar_wait(smem_u32(&ctl->acc_full[ab]), ((uint32_t)(seg / p.acc_bufs)) & 1u);
-      tc_fence_after();
-      if (threadIdx.x == kThreads - 1) TC_STAMP(4);
+      // (PAIR / dual: [cta][slot][half][128][BN])
+      float* pdst = p.part + ((((int64_t)cta * 2 + (ka > 0 ? 0 : 1)) * ((PAIR || dual) ? 2 : 1) + ((PAIR || dual) ? hrank : 0)) * kBM + lg * 32) * p.BN;
+      const uint32_t acc = tmem + (uint32_t)ab * tmem_acc_stride(p.BN, p.passes) + (uint32_t)(g * p.BN) + ((uint32_t)(lg * 32) << 16);
+      __syncwarp();
       for (int j = 0; j < p.BN; j += 32) {
         uint32_t v[32];
         tmem_ld32(acc + (uint32_t)j, v);
@@ -1027,6 +1067,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         }
         __syncwarp();
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -1393,7 +1434,7 @@ bool common_ok(const NvaeConvDesc* d, int which) {
 // Launch plan shared by the three directions: tiles, stages, stream-K grid, partial-buffer size.
 struct Plan {
   PixTile t;
-  int BN, stages, lo_stages, a_tmem, acc_bufs, pair, n_mtiles, n_ntiles, KU, G, njobs, f16, nsub;
+  int BN, stages, lo_stages, a_tmem, acc_bufs, pair, n_mtiles, n_ntiles, KU, G, njobs, f16, nsub, dual;
   size_t pack_bytes;   // 3xFP16: the split B operand (same bytes as the fp32 weights) + 256 for the absmax slots, behind the partials
   uint32_t a_bytes, b_bytes;
   long long U;
@@ -1407,10 +1448,10 @@ struct Plan {
 // fix-up launch, so it is done only when the main loop it shortens is longer than that (small spatial scales:
 // 18-72 tiles, K up to 2304).  Times in microseconds, calibrated on B200 (one 32-deep K stage ~ 0.95 us in
 // 3xTF32, 0.35 us in TF32; fix-up ~ 5 us + partial traffic at ~3 TB/s).
-bool finish_plan(Plan* pl, int passes, bool wgrad) {
+bool finish_plan(Plan* pl, int passes, bool wgrad, bool aligned_k = false) {
   // pair launches: the schedulable tiles are 256-row pair tiles and the workers are the 74 CTA pairs
   const int workers = pl->pair ? kNumSMs / 2 : kNumSMs;
-  const long long T = (long long)(pl->pair ? (pl->n_mtiles + 1) / 2 : pl->n_mtiles) * pl->n_ntiles;
+  const long long T = (long long)((pl->pair || pl->dual) ? (pl->n_mtiles + 1) / 2 : pl->n_mtiles) * pl->n_ntiles;
   pl->U = T * pl->KU;
   const double t_unit = passes == 3 ? (pl->f16 ? 0.5 : 0.95) : 0.35;
   const double slot_us = (double)kBM * pl->BN * 4 * 2 / 3.0e6;  // one partial written + read back
@@ -1423,7 +1464,11 @@ bool finish_plan(Plan* pl, int passes, bool wgrad) {
       if (t < best) { best = t; pl->whole_tiles = 0; pl->G = (int)(S * T); }
     }
   }
-  if (pl->U >= 2 * workers) {  // equal unit ranges over all workers (up to two partials each)
+  // (aligned_k -- backward-filter whose x + dY exceed L2, with fewer tiles than SMs -- keeps the S-way split: its ranges
+  // start at the same pixels in every tile, so the CTAs sweep x / dY in a few aligned phases that L2 holds; equal unit
+  // ranges start anywhere, the working set becomes both whole tensors and every stage goes to HBM: measured 1.13 ms
+  // against 0.75 ms for the 5x5 192 -> 192 layer at 32 x 32)
+  if (pl->U >= 2 * workers && !(aligned_k && T < workers)) {  // equal unit ranges over all workers (up to two partials each)
     const double sk = (double)ceil_div(pl->U, workers) * t_unit + 5.0 + 2.0 * workers * slot_us;
     if (sk < 0.95 * best) { best = sk; pl->whole_tiles = 0; pl->G = workers; }
   }
@@ -1433,7 +1478,7 @@ bool finish_plan(Plan* pl, int passes, bool wgrad) {
   const size_t budget = (size_t)kSmemBudget - 2048;
   size_t lo_slot = 0;
   if (passes == 3) {  // raw ring for the TMA latency + a double-buffered lo ring (wgrad: A and B; fwd/dgrad: B only)
-    pl->a_tmem = (!wgrad || pl->a_bytes == 4u * 32u * 128u) ? 1 : 0;  // wgrad: 32 pixels per stage fit the TMEM A ring
+    pl->a_tmem = (!wgrad || pl->a_bytes == (pl->dual ? 8u : 4u) * 32u * 128u) ? 1 : 0;  // wgrad: 32 pixels per stage fit the TMEM A ring
     lo_slot = pl->f16 ? 0 : (pl->a_tmem ? pl->b_bytes : raw);
     pl->lo_stages = 2;
     pl->acc_bufs = 2;
@@ -1448,6 +1493,12 @@ bool finish_plan(Plan* pl, int passes, bool wgrad) {
         while (deep > 2 && budget < deep * lo_slot + 3 * raw) --deep;
         if (deep > 2) { pl->acc_bufs = 1; pl->lo_stages = deep; }
       }
+    }
+    if (pl->dual) {  // two accumulators (one per M tile) + A slots of 2 x 32 columns
+      pl->acc_bufs = 1;
+      pl->lo_stages = (512 - 2 * pl->BN) / 64;
+      if (pl->lo_stages > 4) pl->lo_stages = 4;
+      if (pl->lo_stages < 2) return false;
     }
     if (pl->nsub == 2) {  // two accumulators side by side fill TMEM up to the A ring: no accumulator double buffer
       pl->acc_bufs = 1;
@@ -1466,7 +1517,7 @@ bool finish_plan(Plan* pl, int passes, bool wgrad) {
   }
   if (pl->stages > kMaxStages) pl->stages = kMaxStages;
   pl->smem = sizeof(SmemCtl) + 1024 + (size_t)pl->stages * raw + (size_t)pl->lo_stages * lo_slot + sizeof(EpiSmem);
-  pl->part_bytes = pl->split ? al256((size_t)pl->G * 2 * (pl->pair ? 2 : 1) * kBM * pl->BN * sizeof(float)) : 0;
+  pl->part_bytes = pl->split ? al256((size_t)pl->G * 2 * ((pl->pair || pl->dual) ? 2 : 1) * kBM * pl->BN * sizeof(float)) : 0;
   return true;
 }
 
@@ -1522,9 +1573,13 @@ bool plan_gemm(const NvaeConvDesc* d, int which, int ntaps, Plan* pl) {
     }
   }
   pl->n_ntiles = (int)ceil_div(n_total, pl->BN);
+  {  // 3xFP16, N <= 192: two M tiles per CTA share each B tile (NVAE_F16X3_DUAL=0 disables)
+    const char* e = getenv("NVAE_F16X3_DUAL");
+    pl->dual = pl->f16 && pl->nsub == 1 && pl->BN <= 192 && pl->n_mtiles >= 2 && !(e != nullptr && e[0] == '0');
+  }
   const int nch = which == 0 ? (int)(ceil_div(d->Cin, kChunk) + ceil_div(d->Cin2, kChunk)) : (int)ceil_div(d->Cout, kChunk);
   pl->KU = ntaps * nch;
-  pl->a_bytes = kBM * 128;
+  pl->a_bytes = (pl->dual ? 2 : 1) * kBM * 128;
   pl->b_bytes = (uint32_t)(pl->pair ? pl->BN / 2 : pl->BN) * 128;  // pair: each CTA stages half of the B tile
   pl->njobs = 0;
   if (!finish_plan(pl, passes, false)) return false;
@@ -1563,11 +1618,17 @@ bool plan_wgrad(const NvaeConvDesc* d, Plan* pl) {
   while (pl->nsub == 1 && (size_t)(4 + pl->BN / kChunk) * KP * 128 * want > (size_t)kSmemBudget - 2048 && pl->BN > 32) pl->BN -= 32;
   pl->n_ntiles = (int)ceil_div(d->Cout, pl->BN);
   pl->KU = pl->t.n_tiles;
-  pl->a_bytes = 4u * KP * 128u;
+  {
+    const char* e = getenv("NVAE_F16X3_DUAL");
+    pl->dual = pl->f16 && pl->nsub == 1 && KP == 32 && pl->BN <= 192 && pl->BN % 64 == 0 && d->Cout % pl->BN == 0 &&
+               pl->n_mtiles >= 2 && !(e != nullptr && e[0] == '0');
+  }
+  pl->a_bytes = (pl->dual ? 8u : 4u) * KP * 128u;
   pl->b_bytes = (uint32_t)(pl->BN / kChunk) * KP * 128u;
   // 3xFP16 needs the TMEM A path (32 pixels per stage) and N tiles made of whole 64-channel chunks
   if (pl->f16 && (KP != 32 || pl->BN % 64 != 0 || d->Cout % pl->BN != 0)) pl->f16 = 0;
-  if (!finish_plan(pl, passes, true)) return false;
+  const double operand_mb = ((double)d->N * d->H * d->W * d->Cin + (double)d->N * d->Ho * d->Wo * d->Cout) * 4e-6;
+  if (!finish_plan(pl, passes, true, pl->f16 && operand_mb > 160.0)) return false;
   if (pl->f16) {
     pl->pack_bytes = al256((size_t)d->N * d->Ho * d->Wo * d->Cout * sizeof(float)) + 256;
     pl->part_bytes += pl->pack_bytes;
@@ -1580,9 +1641,9 @@ void fill_common(TcParams* p, const NvaeConvDesc* d, const Plan& pl, float* part
   p->oH = d->Ho; p->oW = d->Wo; p->os = 1; p->ooh = 0; p->oow = 0;
   p->a5d = 0; p->par_c = d->Cin;
   p->tw = pl.t.tw; p->th = pl.t.th; p->tn = pl.t.tn; p->tiles_h = pl.t.tiles_h;
-  p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->acc_bufs = pl.acc_bufs; p->pair = pl.pair; p->n_mtiles = pl.n_mtiles; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1; p->f16 = pl.f16; p->amax = nullptr; p->nsub = pl.nsub;
+  p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->acc_bufs = pl.acc_bufs; p->pair = pl.pair || pl.dual; p->dual = pl.dual; p->n_mtiles = pl.n_mtiles; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1; p->f16 = pl.f16; p->amax = nullptr; p->nsub = pl.nsub;
   p->n_ntiles = pl.n_ntiles; p->KU = pl.KU; p->U = pl.U;
-  p->T = (pl.pair ? (pl.n_mtiles + 1) / 2 : pl.n_mtiles) * pl.n_ntiles; p->whole_tiles = pl.whole_tiles;
+  p->T = ((pl.pair || pl.dual) ? (pl.n_mtiles + 1) / 2 : pl.n_mtiles) * pl.n_ntiles; p->whole_tiles = pl.whole_tiles;
   p->a_bytes = pl.a_bytes; p->b_bytes = pl.b_bytes;
   p->part = part;
 }
@@ -1651,7 +1712,7 @@ int launch(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t 
     }
     if (fl.n > 0) {
       // few split tiles -> fewer rows per block, so the fix-up still fills the machine
-      const int nrk = pl.pair ? 2 : 1;
+      const int nrk = (pl.pair || pl.dual) ? 2 : 1;
       int rows = 32;
       while (rows > 1 && (long long)fl.n * nrk * (kBM / rows) < 2 * kNumSMs) rows >>= 1;
       nvae::launch(conv_tc_fixup_kernel<WGRAD>, dim3(fl.n, kBM / rows, nrk), kFixThreads, 0, stream, p, pl.G, rows, fl);

@@ -214,7 +214,7 @@ def test_conv2d_stride2_tensor_core(lib_built, case):
 
 
 
-@pytest.mark.parametrize("mode,tol", [("tf32x3", 2e-5), ("f16x3", 2e-5), ("tf32", 3e-3)])
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 2e-5), ("f16x3", 2e-5), ("f16x3-plain", 2e-5), ("tf32", 3e-3)])
 @pytest.mark.parametrize("case", TC_CASES + [(8, 16, 16, 384, 0, 384, 5, True)])
 def test_conv2d_tensor_core_modes(lib_built, case, mode, tol, monkeypatch):
     """tcgen05 implicit-GEMM fwd / dgrad / wgrad against the float64 oracle.  3xTF32 and 3xFP16 (the arithmetic the
@@ -227,10 +227,13 @@ def test_conv2d_tensor_core_modes(lib_built, case, mode, tol, monkeypatch):
     N, Hh, W, Cin, Cin2, Cout, k, residual = case
     if len(case) == 8 and Cin == 384 and mode == "tf32":
         pytest.skip("large case: 3xTF32 / 3xFP16 only")
-    prec = {"tf32x3": _lib.NVAE_PREC_TF32X3, "f16x3": _lib.NVAE_PREC_TF32X3, "tf32": _lib.NVAE_PREC_TF32}[mode]
-    monkeypatch.setenv("NVAE_F16X3", "1" if mode == "f16x3" else "0")
+    prec = _lib.NVAE_PREC_TF32 if mode == "tf32" else _lib.NVAE_PREC_TF32X3
+    monkeypatch.setenv("NVAE_F16X3", "1" if mode.startswith("f16x3") else "0")
     monkeypatch.setenv("NVAE_F16X3_MIN_GFLOP", "0")
-    xs, dys = (300.0, 1e-5) if mode == "f16x3" else (1.0, 1.0)
+    # f16x3: two M tiles per CTA (N <= 192) / two accumulators per tile (N <= 384); -plain: one tile, one accumulator
+    monkeypatch.setenv("NVAE_F16X3_DUAL", "0" if mode == "f16x3-plain" else "1")
+    monkeypatch.setenv("NVAE_F16X3_NSUB", "0" if mode == "f16x3-plain" else "1")
+    xs, dys = (300.0, 1e-5) if mode.startswith("f16x3") else (1.0, 1.0)
     rng = np.random.default_rng(5)
     with R.Runtime(seed=7, precision=prec) as rt:
         conv = Conv2D(Cout, (k, k), padding="same", in_channels=Cin + Cin2, name="c")
