@@ -156,6 +156,10 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # roofline of the dominant kernel, measured live
 # ------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant 3xFP16 launch (profiles/r01i_ncu_conv_f16_5x5_384.md)
+DOMINANT_TRAFFIC_F16 = 104.1e6
+
+
 def measure_dominant_kernel(model, reps=5):
     """Largest forward conv of the step: postprocess cbs2, 5x5, 384->384 at 16x16, batch 144
     (GEMM M=36864, N=384, K=9600; 2MNK = 271.8 GFLOP per launch).  Timed alone, L2 flushed between reps."""
@@ -284,29 +288,36 @@ def main():
     dom = measure_dominant_kernel(model)["conv_fwd"]
     tc = precision != _lib.NVAE_PREC_FP32
     x3 = precision == _lib.NVAE_PREC_TF32X3
+    # NVAE_PREC_TF32X3 runs its large GEMMs (this one included) as 3xFP16 on kind::f16 unless NVAE_F16X3=0
+    f16 = x3 and os.environ.get("NVAE_F16X3", "1") != "0"
     bf16_peak = peaks.get("bf16_tflops", 1590.0)
-    peak = bf16_peak / 2.0  # TF32 = half the bf16 rate (nominal ratio) of the measured/fallback bf16 burst figure
+    # kind::f16 runs at the dense bf16/fp16 rate (the measured cuBLAS figure); kind::tf32 at half of it (nominal ratio)
+    peak = bf16_peak if f16 else bf16_peak / 2.0
     achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
+    arith = ("3xFP16: amax-scaled fp16 hi/lo split, A via TMEM, pre-split B via TMA, two accumulators per CTA" if f16 else
+             "3xTF32 split in-kernel, A via TMEM" if x3 else "single-pass TF32")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01h_ncu_*.md);
-                # algorithmic bytes are 127.9 MB (x + w + y once)
-                "traffic": 113.3e6 if x3 else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01i_ncu_*.md /
+                # r01h for 3xTF32); algorithmic bytes are 127.9 MB (x + w + y once)
+                "traffic": DOMINANT_TRAFFIC_F16 if f16 else (113.3e6 if x3 else None),
                 "mma_issue_factor": 3 if x3 else 1,
-                "note": ("3xTF32 issues 3 MMAs per algorithmic product, so its ceiling is peak/3; "
-                         "frac is algorithmic FLOP/s over the full TF32 peak") if x3 else "",
-                "kernel": ("conv_tc_kernel<false> (tcgen05 kind::tf32 implicit GEMM, TMA-staged, "
-                           + ("3xTF32 split in-kernel, A via TMEM" if x3 else "single-pass TF32") + ")" if tc else
-                           "simt_conv_kernel<FwdProb> (fp32 CUDA-core implicit GEMM)"),
+                "issued_mma_frac": (3 if x3 else 1) * achieved / peak,
+                "note": ("fp32-grade products cost 3 MMAs each (hi*hi + hi*lo + lo*hi), so the ceiling of frac is 1/3; "
+                         "issued_mma_frac is the tensor pipe's own utilisation against the same peak") if x3 else "",
+                "kernel": ("conv_tc_kernel<false> (tcgen05 " + ("kind::f16" if f16 else "kind::tf32") +
+                           " implicit GEMM, TMA-staged, " + arith + ")" +
+                           (" + absmax2_kernel + f16_pack_b_kernel (operand scales / B split, inside ms_per_launch)" if f16 else "")
+                           if tc else "simt_conv_kernel<FwdProb> (fp32 CUDA-core implicit GEMM)"),
                 "shape": "postprocess cbs2 5x5 384->384 @16x16, batch 144: M=36864 N=384 K=9600",
                 "flops_per_launch": dom["flops"], "ms_per_launch": dom["ms"],
-                "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst) / 2 for TF32" if peaks else
-                                "fallback 1590 bf16 TFLOP/s / 2 for TF32"),
+                "peak_source": (("MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590 bf16 TFLOP/s") +
+                                ("" if f16 else " / 2 for TF32")),
                 "step_tensor_frac": (FLOP_PER_IMAGE * B / ((ms / args.steps) * 1e-3) / 1e12) /
-                                    (peaks.get("bf16_tflops_sustained", 1400.0) / 2.0)}
+                                    (peaks.get("bf16_tflops_sustained", 1400.0) / (1.0 if f16 else 2.0))}
     cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(args.cpu_batch)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": ("tf32x3" if x3 else "tf32") if tc else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": ("f16x3+tf32x3" if f16 else "tf32x3" if x3 else "tf32") if tc else "f32", "data": "synthetic",
             "config": {"workload": "full MNIST-config NVAE train step (train.py defaults: 40.1M params, 15 latent "
                                    "groups, KL+recon+BN-gamma loss, SN, Adamax), BASELINE configs[2]",
                        "batch_per_gpu": B, "global_batch": B * world, "image": "32x32x1",

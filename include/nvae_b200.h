@@ -45,8 +45,12 @@ enum { NVAE_ACT_NONE = 0, NVAE_ACT_SWISH = 1, NVAE_ACT_ELU = 2 };
 
 /* Arithmetic of the convolution GEMMs. FP32 = CUDA-core FFMA; TF32 = one tcgen05 kind::tf32 MMA per operand
  * pair, operands rounded to TF32 by their producers (10-bit mantissa: ~5e-4 per conv, NOT within the 1e-3
- * whole-model parity bound); TF32X3 = 3xTF32 split inside the kernel (a_hi*b_lo + a_lo*b_hi + a_hi*b_hi on the
- * tensor cores, fp32-level accuracy: the default and the mode every parity claim is made in). */
+ * whole-model parity bound); TF32X3 = split-operand products a_hi*b_hi + a_hi*b_lo + a_lo*b_hi on the tensor cores,
+ * fp32-level accuracy (22 significant bits per operand): the default and the mode every parity claim is made in.
+ * The split is 3xTF32 inside the kernel for most convolutions and, for the large stride-1 GEMMs (>= 20 GFLOP per
+ * launch; NVAE_F16X3=0 turns it off, NVAE_F16X3_MIN_GFLOP moves the threshold), 3xFP16: both operands are scaled by
+ * a power of two taken from their absmax (computed into the workspace just before the launch) so the fp16 high and
+ * low parts stay in range, multiplied with kind::f16 at twice the TF32 rate, and the epilogue undoes the scales. */
 enum { NVAE_PREC_FP32 = 0, NVAE_PREC_TF32 = 1, NVAE_PREC_TF32X3 = 2 };
 
 /* Library / device identification. Returns 100 for sm_100; build id string is static. */

@@ -455,7 +455,7 @@ __device__ __forceinline__ float4 tf32_lo4(const float4& v) {
 __device__ __forceinline__ int f16_exp(float amax) {
   int e = 0;
   if (amax > 0.f && amax < 3.0e38f) (void)frexpf(amax, &e);
-  return e;
+  return e < -100 ? -100 : e;  // (a denormal absmax would ask for a scale beyond fp32's range)
 }
 __device__ __forceinline__ float f16_in_scale(float amax) { return amax > 0.f ? ldexpf(1.f, 15 - f16_exp(amax)) : 1.f; }
 __device__ __forceinline__ float f16_out_scale(const float* amax) {

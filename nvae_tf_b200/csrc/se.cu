@@ -150,21 +150,34 @@ __global__ void __launch_bounds__(kSeThreads) se_bwd_gate_kernel(
   }
 }
 
-// dense-layer gradients: fixed-order sums over the batch (deterministic).  Four interleaved partial sums per
-// output so four pairs of loads are in flight (a single dependent chain made this kernel latency-bound).
-__device__ __forceinline__ float se_dot_batch(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
-                                              int B) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int i = 0;
-  for (; i + 3 < B; i += 4) {
-    const float a0 = __ldg(a + (int64_t)i * lda), a1 = __ldg(a + (int64_t)(i + 1) * lda),
-                a2 = __ldg(a + (int64_t)(i + 2) * lda), a3 = __ldg(a + (int64_t)(i + 3) * lda);
-    const float b0 = b ? __ldg(b + (int64_t)i * ldb) : 1.f, b1 = b ? __ldg(b + (int64_t)(i + 1) * ldb) : 1.f,
-                b2 = b ? __ldg(b + (int64_t)(i + 2) * ldb) : 1.f, b3 = b ? __ldg(b + (int64_t)(i + 3) * ldb) : 1.f;
-    s0 = fmaf(a0, b0, s0); s1 = fmaf(a1, b1, s1); s2 = fmaf(a2, b2, s2); s3 = fmaf(a3, b3, s3);
+// dense-layer gradients: fixed-order sums over the batch (deterministic).  Each output is owned by 8 adjacent lanes
+// that take interleaved batch elements (b = sub, sub + 8, ...), six pairs of loads in flight per lane, and are combined
+// by a fixed xor-shuffle tree.  (One thread per output walking the whole batch was a chain of B/4 dependent L2 round
+// trips: 20 us for 8 500 dot products of length 144.)
+__device__ __forceinline__ float se_dot_batch8(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                               int B, int sub) {
+  float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int i = sub;
+  for (; i + 40 < B; i += 48) {
+    float av[6], bv[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      av[j] = __ldg(a + (int64_t)(i + 8 * j) * lda);
+      bv[j] = b ? __ldg(b + (int64_t)(i + 8 * j) * ldb) : 1.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) s[j] = fmaf(av[j], bv[j], s[j]);
   }
-  for (; i < B; ++i) s0 = fmaf(__ldg(a + (int64_t)i * lda), b ? __ldg(b + (int64_t)i * ldb) : 1.f, s0);
-  return (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {  // at most five elements are left per lane
+    const int ii = i + 8 * j;
+    if (ii < B) s[j] = fmaf(__ldg(a + (int64_t)ii * lda), b ? __ldg(b + (int64_t)ii * ldb) : 1.f, s[j]);
+  }
+  float r = ((s[0] + s[1]) + (s[2] + s[3])) + (s[4] + s[5]);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 4);
+  return r;
 }
 
 __global__ void se_bwd_weights_kernel(const float* __restrict__ pooled, const float* __restrict__ hidden,
@@ -173,21 +186,29 @@ __global__ void se_bwd_weights_kernel(const float* __restrict__ pooled, const fl
                                       float* __restrict__ dw2, float* __restrict__ db2) {
   nvae::pdl_enter();
   const int n1 = C * hid, total = 2 * n1 + C + hid;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    if (i < n1) {  // dw2[j][c]
-      const int j = i / C, c = i % C;
-      dw2[i] = se_dot_batch(hidden + j, hid, dz2 + c, C, B);
-    } else if (i < 2 * n1) {  // dw1[c][j]
-      const int k = i - n1, c = k / hid, j = k % hid;
-      dw1[k] = se_dot_batch(pooled + c, C, dh + j, hid, B);
-    } else if (i < 2 * n1 + C) {
-      const int c = i - 2 * n1;
-      db2[c] = se_dot_batch(dz2 + c, C, nullptr, 0, B);
-    } else {
-      const int j = i - 2 * n1 - C;
-      db1[j] = se_dot_batch(dh + j, hid, nullptr, 0, B);
-    }
+  const int sub = threadIdx.x & 7;
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const bool valid = i0 < total;
+  const int i = valid ? i0 : total - 1;  // whole warps reach the shuffles
+  const float* a;
+  const float* b = nullptr;
+  float* out;
+  int lda, ldb = 0;
+  if (i < n1) {  // dw2[j][c]
+    const int j = i / C, c = i % C;
+    a = hidden + j; lda = hid; b = dz2 + c; ldb = C; out = dw2 + i;
+  } else if (i < 2 * n1) {  // dw1[c][j]
+    const int k = i - n1, c = k / hid, j = k % hid;
+    a = pooled + c; lda = C; b = dh + j; ldb = hid; out = dw1 + k;
+  } else if (i < 2 * n1 + C) {
+    const int c = i - 2 * n1;
+    a = dz2 + c; lda = C; out = db2 + c;
+  } else {
+    const int j = i - 2 * n1 - C;
+    a = dh + j; lda = hid; out = db1 + j;
   }
+  const float r = se_dot_batch8(a, lda, b, ldb, B, sub);
+  if (valid && sub == 0) *out = r;
 }
 
 // dt' = beta*dy*gate + dpool/HW ; dxres (+)= alpha*dy
@@ -265,7 +286,7 @@ extern "C" int nvae_se_bwd(const float* dy, const float* t, const float* stat, i
   nvae::launch(se_bwd_gate_kernel, B, kSeThreads, 0, stream, dy, t, stat, HW, C, hid, w1, w2, hidden, gate, beta, dz2, dh, dpool);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   const int total = 2 * C * hid + C + hid;
-  nvae::launch(se_bwd_weights_kernel, (total + 127) / 128, 128, 0, stream, pooled, hidden, dz2, dh, B, C, hid, dw1, db1, dw2, db2);
+  nvae::launch(se_bwd_weights_kernel, (total * 8 + 127) / 128, 128, 0, stream, pooled, hidden, dz2, dh, B, C, hid, dw1, db1, dw2, db2);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   const int64_t n4 = (int64_t)B * HW * (C / 4);
   nvae::launch(se_bwd_apply_kernel, se_grid(n4, 256), 256, 0, stream, dy, gate, dpool, n4, C / 4, (int64_t)HW * (C / 4),
