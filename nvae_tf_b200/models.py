@@ -15,6 +15,7 @@ Two things Keras leaves implicit are explicit arguments here:
 """
 from __future__ import annotations
 
+import os
 import math
 from typing import Dict, List, Optional
 
@@ -237,7 +238,11 @@ class NVAE:
             raise RuntimeError("graph capture draws epsilon on device (Philox); clear the injected epsilons")
         world = torch.distributed.get_world_size(self.process_group) if torch.distributed.is_initialized() else 1
         in_graph = world == 1
-        stream = torch.cuda.Stream(device=rt.device)
+        # the main chain (forward, dgrad, BN / SE backward) is the critical path; the weight-gradient side stream only
+        # has to finish by the optimizer.  A high-priority capture stream makes the captured kernel nodes win the CTA
+        # scheduler whenever both have work (NVAE_STREAM_PRIO=0: equal priorities)
+        prio = -1 if os.environ.get("NVAE_STREAM_PRIO", "1") != "0" else 0
+        stream = torch.cuda.Stream(device=rt.device, priority=prio)
         stream.wait_stream(torch.cuda.current_stream(rt.device))
         with torch.cuda.stream(stream):
             for _ in range(warmup):
