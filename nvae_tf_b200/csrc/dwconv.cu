@@ -15,7 +15,7 @@ struct DwGeom {
   size_t smem_tile;  // floats
 };
 
-constexpr size_t kDwTileBytes = 44 * 1024;  // haloed tile budget: small tiles -> 3-4 CTAs per SM, loads overlap compute
+constexpr size_t kDwTileBytes = 36 * 1024;  // haloed tile budget: two buffers x 3 CTAs per SM fit the 227 KB of an SM
 
 static DwGeom dw_geom(int N, int H, int W, int C) {
   DwGeom g;
@@ -78,12 +78,15 @@ __device__ __forceinline__ void dw_stage(float* tile, const float* __restrict__ 
   __syncthreads();
 }
 
-// FLIP=false: y = dwconv(act(bn(x))) + bias.   FLIP=true: da = dwconv_transpose(dy) (no prologue, no bias)
+// One-tile-per-CTA variant (the forward direction): y = dwconv(act(bn(x))) + bias with the BatchNorm-apply + activation
+// applied in REGISTERS between the global load and the shared-memory store.  (The persistent cp.async kernel below has to
+// activate in place in shared memory after the copies land, which measured slower for the forward direction: 45 vs 40 us
+// at [144,8,8,768]; for the prologue-free backward-data direction it is the faster one, 31 vs 33 us / 64 vs 74 us.)
 // Compute mapping: a warp is the 32 channels of the chunk at one work item, a thread is ONE channel: its 25 taps
 // live in registers, shared-memory reads and global stores are 128-byte rows (conflict-free, fully coalesced),
 // and each thread produces a 2 x 4 output patch from a 6 x 8 input window (0.24 shared loads per FMA).
 template <bool FLIP>
-__global__ void __launch_bounds__(kDwThreads, 3) dwconv5x5_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(kDwThreads, 3) dwconv5x5_tile_kernel(const float* __restrict__ x,
                                                                   const float* __restrict__ stat, int act, int N, int H,
                                                                   int W, int C, const float* __restrict__ wts,
                                                                   const float* __restrict__ bias, float* __restrict__ y,
@@ -133,6 +136,155 @@ __global__ void __launch_bounds__(kDwThreads, 3) dwconv5x5_kernel(const float* _
         if (w0 + j < W) yo[(int64_t)j * C] = acc[o][j];
     }
   }
+}
+
+// FLIP=false: y = dwconv(act(bn(x))) + bias.   FLIP=true: da = dwconv_transpose(dy) (no prologue, no bias)
+// Persistent + pipelined: a CTA owns one 32-channel chunk (its 25 taps stay in registers) and walks image groups with
+// a DOUBLE-BUFFERED haloed tile: while the warps compute group g from one buffer, cp.async (16-byte, L2 -> shared
+// memory, no registers) is already filling the other with group g + gridDim.y, so global loads are in flight for the
+// whole lifetime of the CTA instead of only during a short staging phase (the one-tile-per-CTA version spent most of
+// each CTA's ~10 us on dependent latencies: 22-26 % of the HBM peak).  The halo of both buffers is zeroed once; the
+// BatchNorm-apply + activation runs in place on the elements each thread copied itself.
+// Compute mapping: a warp is the 32 channels of the chunk at one work item, a thread is ONE channel: shared-memory
+// reads and global stores are 128-byte rows (conflict-free, fully coalesced), and each thread produces a 2 x 4 output
+// patch from a 6 x 8 input window (0.24 shared loads per FMA).
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The tile geometry is the same for every group a CTA walks, so everything index-shaped is decoded ONCE per CTA into
+// registers: the shared-memory offset of each pixel this thread copies (its global offset is just p * C), and the
+// (window, output) offsets of each work item this warp computes.  The per-group loops are then copies / FMAs only
+// (the integer divisions of the first version were a third of all issued instructions; ncu: issue-bound at 64 %).
+constexpr int kDwMaxCopies = 10;  // pixels per thread: ceil(288 / 32) for the largest tile
+constexpr int kDwMaxItems = 4;    // work items per warp: ceil(32 / 8)
+
+template <bool FLIP>
+__global__ void __launch_bounds__(kDwThreads, 3) dwconv5x5_kernel(const float* __restrict__ x,
+                                                                  const float* __restrict__ stat, int act, int N, int H,
+                                                                  int W, int C, const float* __restrict__ wts,
+                                                                  const float* __restrict__ bias, float* __restrict__ y,
+                                                                  int imgs, int ngroups, int WQ, int PH, int PW) {
+  nvae::pdl_enter();
+  extern __shared__ __align__(16) float smem[];
+  const int tile_floats = imgs * PH * PW * kDwCC;
+  const int c0 = blockIdx.x * kDwCC;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c4 = threadIdx.x & 7;
+  const int HW = H * W, HP = (H + 1) >> 1;
+  // zero both buffers once: the halo stays zero, the interiors are overwritten by every group's copies
+  for (int i = threadIdx.x; i < 2 * tile_floats / 4; i += kDwThreads) reinterpret_cast<float4*>(smem)[i] = make_float4(0, 0, 0, 0);
+  float wreg[25];
+#pragma unroll
+  for (int t = 0; t < 25; ++t) wreg[t] = __ldg(wts + (int64_t)(FLIP ? 24 - t : t) * C + c0 + lane);
+  const float bv = (!FLIP && bias != nullptr) ? __ldg(bias + c0 + lane) : 0.f;
+  float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0);
+  const bool prologue = !FLIP && stat != nullptr;
+  if (prologue) {
+    sc = ldg4(stat + 2 * C + c0 + c4 * 4);
+    sh = ldg4(stat + 3 * C + c0 + c4 * 4);
+  }
+  const bool activate = prologue || (!FLIP && act != NVAE_ACT_NONE);
+  // copy k of this thread: pixel p = (tid >> 3) + 32 k of the group -> shared-memory float offset (-1: none)
+  int soff[kDwMaxCopies];
+#pragma unroll
+  for (int k = 0; k < kDwMaxCopies; ++k) {
+    const int p = (threadIdx.x >> 3) + k * (kDwThreads >> 3);
+    const int im = p / HW, q = p - im * HW, h = q / W, w = q - h * W;
+    soff[k] = p < imgs * HW ? ((im * PH + h + 2) * PW + w + 2) * kDwCC + c4 * 4 : -1;
+  }
+  // work item m of this warp: it = warp + 8 m -> window offset in the tile, output offset in the group, image, h0, w0
+  // (kept in shared memory: the item loop is not unrolled -- four copies of its 200-FMA body would not fit the
+  // instruction cache -- and a register table cannot be indexed dynamically)
+  __shared__ int itab[kDwThreads / 32][kDwMaxItems][3];
+  if (lane < kDwMaxItems) {
+    const int it = warp + lane * (kDwThreads / 32);
+    const int wq = it % WQ, t = it / WQ, hp = t % HP, im = t / HP;
+    const int h0 = hp * 2, w0 = wq * kDwTW;
+    itab[warp][lane][0] = ((im * PH + h0) * PW + w0) * kDwCC;
+    itab[warp][lane][1] = ((im * H + h0) * W + w0) * C;
+    itab[warp][lane][2] = it < imgs * HP * WQ ? (im << 16) | (h0 << 8) | w0 : -1;
+  }
+  __syncthreads();
+  const float* xc = x + c0 + c4 * 4;
+  float* yc = y + c0 + lane;
+  const int p0 = threadIdx.x >> 3;
+  auto issue = [&](float* tile, int g) {
+    const int n0 = g * imgs;
+    const int npix = ((N - n0) < imgs ? (N - n0) : imgs) * HW;
+    const float* xb = xc + (int64_t)n0 * HW * C;
+#pragma unroll
+    for (int k = 0; k < kDwMaxCopies; ++k) {
+      const int p = p0 + k * (kDwThreads >> 3);
+      if (soff[k] >= 0 && p < npix) cp_async16(tile + soff[k], xb + (int64_t)p * C);
+    }
+  };
+  int g = blockIdx.y, buf = 0;
+  if (g < ngroups) issue(smem, g);
+  cp_async_commit();
+  for (; g < ngroups; g += gridDim.y, buf ^= 1) {
+    float* tile = smem + (size_t)buf * tile_floats;
+    const int n0 = g * imgs;
+    const int nimg = (N - n0) < imgs ? (N - n0) : imgs;
+    // next group -> the other buffer (its readers finished at the barrier that ended the last pass)
+    if (g + (int)gridDim.y < ngroups) issue(smem + (size_t)(buf ^ 1) * tile_floats, g + gridDim.y);
+    cp_async_commit();
+    cp_async_wait<1>();  // this group's copies have landed (only the newest commit may be pending)
+    if (activate) {      // act(x * scale + shift) in place on exactly the elements this thread copied itself
+      const int npix = nimg * HW;
+#pragma unroll
+      for (int k = 0; k < kDwMaxCopies; ++k) {
+        if (soff[k] >= 0 && p0 + k * (kDwThreads >> 3) < npix) {
+          float4* e = reinterpret_cast<float4*>(tile + soff[k]);
+          float4 v = *e;
+          v.x = act_fwd_rt(fmaf(v.x, sc.x, sh.x), act); v.y = act_fwd_rt(fmaf(v.y, sc.y, sh.y), act);
+          v.z = act_fwd_rt(fmaf(v.z, sc.z, sh.z), act); v.w = act_fwd_rt(fmaf(v.w, sc.w, sh.w), act);
+          *e = v;
+        }
+      }
+    }
+    __syncthreads();
+    float* yg = yc + (int64_t)n0 * HW * C;
+#pragma unroll 1
+    for (int m = 0; m < kDwMaxItems; ++m) {
+      const int code = itab[warp][m][2];
+      if (code < 0 || (code >> 16) >= nimg) break;  // items are ordered by image
+      const int h0 = (code >> 8) & 0xff, w0 = code & 0xff;
+      float acc[2][kDwTW];
+#pragma unroll
+      for (int j = 0; j < kDwTW; ++j) { acc[0][j] = bv; acc[1][j] = bv; }
+      const float* trow = tile + itab[warp][m][0] + lane;
+#pragma unroll
+      for (int ri = 0; ri < 6; ++ri) {
+        if (ri == 5 && h0 + 1 >= H) break;  // the sixth window row only feeds the second output row
+        float win[kDwTW + 4];
+#pragma unroll
+        for (int j = 0; j < kDwTW + 4; ++j) win[j] = trow[(ri * PW + j) * kDwCC];
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const int tr = ri - o;
+          if (tr < 0 || tr > 4) continue;
+#pragma unroll
+          for (int s = 0; s < 5; ++s)
+#pragma unroll
+            for (int j = 0; j < kDwTW; ++j) acc[o][j] = fmaf(win[j + s], wreg[tr * 5 + s], acc[o][j]);
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        if (h0 + o >= H) break;
+        float* yo = yg + itab[warp][m][1] + (int64_t)o * W * C;
+#pragma unroll
+        for (int j = 0; j < kDwTW; ++j)
+          if (w0 + j < W) yo[(int64_t)j * C] = acc[o][j];
+      }
+    }
+    __syncthreads();  // every warp is done with this buffer before the next pass refills it
+  }
+  cp_async_wait<0>();
 }
 
 // Backward-filter: dw[tap][c] = sum_pix a[pix + tap][c] * dy[pix][c], db[c] = sum dy.  A thread is one channel (a
@@ -230,6 +382,9 @@ static int dw_check(int N, int H, int W, int C) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % kDwCC)) return NVAE_E_BADSHAPE;
   DwGeom g = dw_geom(N, H, W, C);
   if ((g.smem_tile * 2 + 26 * kDwCC * 8) * sizeof(float) > 200 * 1024) return NVAE_E_UNSUPPORTED;
+  if (g.imgs * H * W > kDwMaxCopies * (kDwThreads >> 3) || g.imgs * ((H + 1) / 2) * g.WQ > kDwMaxItems * (kDwThreads / 32) ||
+      H > 255 || W > 255)
+    return NVAE_E_UNSUPPORTED;  // per-thread copy / per-warp item tables of dwconv5x5_kernel
   return NVAE_OK;
 }
 
@@ -241,14 +396,29 @@ template <bool FLIP>
 static int dw_launch(const float* x, const float* stat, int act, int N, int H, int W, int C, const float* w,
                      const float* bias, float* y, cudaStream_t stream) {
   DwGeom g = dw_geom(N, H, W, C);
-  const size_t smem = g.smem_tile * sizeof(float);
+  if (!FLIP) {  // forward: one tile per CTA, activation in registers
+    const size_t smem1 = g.smem_tile * sizeof(float);
+    static bool configured1 = false;
+    if (!configured1) {
+      NVAE_CUDA_TRY(cudaFuncSetAttribute(dwconv5x5_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured1 = true;
+    }
+    nvae::launch(dwconv5x5_tile_kernel<false>, dim3(g.nchunks, g.ngroups), kDwThreads, smem1, stream, x, stat, act, N, H, W, C, w,
+                 bias, y, g.imgs, g.WQ, g.PH, g.PW);
+    NVAE_RETURN_IF_LAUNCH_FAILED();
+    return NVAE_OK;
+  }
+  const size_t smem = 2 * g.smem_tile * sizeof(float);  // double buffer
   static size_t configured[2] = {0, 0};
   if (smem > configured[FLIP]) {
     NVAE_CUDA_TRY(cudaFuncSetAttribute(dwconv5x5_kernel<FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured[FLIP] = 200 * 1024;
   }
-  nvae::launch(dwconv5x5_kernel<FLIP>, dim3(g.nchunks, g.ngroups), kDwThreads, smem, stream, x, stat, act, N, H, W, C, w, bias, y,
-                                                                                   g.imgs, g.WQ, g.PH, g.PW);
+  // persistent: ~3 CTAs per SM in total, each walking its chunk's image groups
+  int gy = (int)ceil_div(3 * kNumSMs, g.nchunks);
+  if (gy > g.ngroups) gy = g.ngroups;
+  nvae::launch(dwconv5x5_kernel<FLIP>, dim3(g.nchunks, gy), kDwThreads, smem, stream, x, stat, act, N, H, W, C, w, bias, y,
+               g.imgs, g.ngroups, g.WQ, g.PH, g.PW);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }

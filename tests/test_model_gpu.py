@@ -131,9 +131,13 @@ def test_full_step_against_golden_fixture(lib_built, name):
     assert m.steps == steps + 1
 
 
-@pytest.mark.parametrize("batch,steps,training", [(6, 20000, True), (5, 80000, False)])
-def test_default_config_step_against_live_oracle(lib_built, batch, steps, training):
-    """train.py defaults (40.1 M parameters, 15 latent groups), small batch so the float64 oracle runs in seconds."""
+@pytest.mark.parametrize("batch,steps,training,f16x3", [(6, 20000, True, False), (5, 80000, False, False),
+                                                        (6, 20000, True, True)])
+def test_default_config_step_against_live_oracle(lib_built, batch, steps, training, f16x3, monkeypatch):
+    """train.py defaults (40.1 M parameters, 15 latent groups), small batch so the float64 oracle runs in seconds.
+    f16x3: every eligible convolution is forced onto the 3xFP16 path the batch-144 step uses for its six large GEMMs
+    (at this batch none would reach the 20 GFLOP threshold), so the arithmetic is checked through the whole model."""
+    monkeypatch.setenv("NVAE_F16X3_MIN_GFLOP", "0" if f16x3 else "1e9")
     cfg = O.NVAEConfig()
     params, trainable, bnl, s = O.build_params(cfg, seed=1, jitter=0.05)
     params = {k: f32(v) for k, v in params.items()}
