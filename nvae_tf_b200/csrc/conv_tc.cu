@@ -416,7 +416,12 @@ __device__ __forceinline__ void store4(const TcParams& p, const RowCtx& r, int n
   if (p.f16) { o.x *= oscale; o.y *= oscale; o.z *= oscale; o.w *= oscale; }
   if (WGRAD) {
     if (n >= p.Cout) return;
-    stg4(p.out1 + r.base * p.Cout + n, o);
+    float* dst = p.out1 + r.base * p.Cout + n;
+    if (p.accumulate) {  // a later batch chunk of a chunked backward-filter call
+      const float4 b = *reinterpret_cast<const float4*>(dst);
+      o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+    }
+    stg4(dst, o);
     return;
   }
   if (n >= p.n_valid) return;
@@ -1736,9 +1741,20 @@ bool nvae_conv_tc_supported(const NvaeConvDesc* d, int which) {
   return plan_gemm(d, which, d->R * d->S, &pl);
 }
 
+static int wgrad_chunks(const NvaeConvDesc* d);
+
 size_t nvae_conv_tc_ws_bytes(const NvaeConvDesc* d, int which) {
   Plan pl;
-  if (which == 2) return plan_wgrad(d, &pl) ? pl.part_bytes : 0;
+  if (which == 2) {
+    size_t b = plan_wgrad(d, &pl) ? pl.part_bytes : 0;
+    const int nc = wgrad_chunks(d);
+    if (nc > 1) {
+      NvaeConvDesc s = *d;
+      s.N = d->N / nc;
+      if (plan_wgrad(&s, &pl) && pl.part_bytes > b) b = pl.part_bytes;
+    }
+    return b;
+  }
   if (which == 1 && d->stride == 2) {
     size_t mx = 0;
     if (!common_ok(d, 1)) return 0;
@@ -1855,8 +1871,46 @@ int nvae_conv2d_dgrad_tc(const NvaeConvDesc* d, const float* dy, const float* w_
   return NVAE_OK;
 }
 
+// The large 3xFP16 filter gradients run on the weight-gradient side stream as persistent 148-CTA kernels that own all of
+// shared memory for 0.6-0.75 ms: any convolution the (high-priority) main chain reaches meanwhile cannot start until they
+// exit.  Cutting the batch into chunks (dW accumulated across them) bounds that wait to one chunk, so the side stream only
+// fills the gaps in which the main stream runs its BatchNorm / SE / depthwise kernels.  Opt-in, NVAE_WGRAD_CHUNKS=n:
+// measured 31.1 (4 chunks) / 31.6 (2) / 31.8 (6) vs 31.7 ms/step unchunked -- within run-to-run noise, because the step
+// is power-capped: overlapping more work does not raise the clock-limited throughput.  Default 1.
+static int wgrad_chunks(const NvaeConvDesc* d) {
+  if (!use_f16x3(d, 2) || d->Cin2 != 0 || d->y_off != 0) return 1;
+  const char* e = getenv("NVAE_WGRAD_CHUNKS");
+  int c = e != nullptr ? atoi(e) : 1;
+  if (c < 1) c = 1;
+  while (c > 1) {
+    NvaeConvDesc s = *d;
+    s.N = d->N / c;
+    if (d->N % c == 0 && use_f16x3(&s, 2)) break;  // the chunk must itself be a large 3xFP16 problem
+    --c;
+  }
+  return c;
+}
+
+static int wgrad_tc_once(const NvaeConvDesc* d, const float* x, const float* x2, const float* dy, float* dw, void* ws,
+                         size_t ws_bytes, cudaStream_t stream, int accumulate);
+
 int nvae_conv2d_wgrad_tc(const NvaeConvDesc* d, const float* x, const float* x2, const float* dy, float* dw, void* ws,
                          size_t ws_bytes, cudaStream_t stream) {
+  const int nc = wgrad_chunks(d);
+  if (nc == 1) return wgrad_tc_once(d, x, x2, dy, dw, ws, ws_bytes, stream, 0);
+  NvaeConvDesc s = *d;
+  s.N = d->N / nc;
+  const int ld = d->y_ld > 0 ? d->y_ld : d->Cout;
+  for (int c = 0; c < nc; ++c) {
+    const int rc = wgrad_tc_once(&s, x + (size_t)c * s.N * d->H * d->W * d->Cin, nullptr,
+                                 dy + (size_t)c * s.N * d->Ho * d->Wo * ld, dw, ws, ws_bytes, stream, c > 0);
+    if (rc) return rc;
+  }
+  return NVAE_OK;
+}
+
+static int wgrad_tc_once(const NvaeConvDesc* d, const float* x, const float* x2, const float* dy, float* dw, void* ws,
+                         size_t ws_bytes, cudaStream_t stream, int accumulate) {
   Plan pl;
   if (!plan_wgrad(d, &pl)) return NVAE_E_UNSUPPORTED;
   if (!aligned16(x) || !aligned16(x2) || !aligned16(dy) || !aligned16(dw) || !aligned16(ws)) return NVAE_E_UNSUPPORTED;
@@ -1872,6 +1926,7 @@ int nvae_conv2d_wgrad_tc(const NvaeConvDesc* d, const float* x, const float* x2,
   p.njobs = pl.njobs;
   p.Cin = d->Cin; p.Cin2 = d->Cin2; p.Ct = Ct; p.Cout = d->Cout;
   p.out1 = dw;
+  p.accumulate = accumulate;
   p.a5d = d->stride == 2;
   TmapSet maps;
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
