@@ -8,16 +8,18 @@ namespace nvae {
 constexpr int kSeThreads = 256;
 constexpr int kSeMaxC = 1024;
 constexpr int kSeMaxHid = 64;
+constexpr size_t kSeFuseBytes = 64 * 1024;  // per-sample tensor size up to which the per-sample CTA also applies the gate
 
 // One CTA per sample: pooled' = affine(mean_hw t), hidden = relu(W1^T pooled' + b1),
 // gate = sigmoid(W2^T hidden + b2).
 __global__ void __launch_bounds__(kSeThreads) se_pool_gate_kernel(
     const float* __restrict__ t, const float* __restrict__ stat, int HW, int C, int hid, const float* __restrict__ w1,
     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-    float* __restrict__ pooled, float* __restrict__ hidden, float* __restrict__ gate) {
+    float* __restrict__ pooled, float* __restrict__ hidden, float* __restrict__ gate, const float* __restrict__ xres,
+    float alpha, float beta, float* __restrict__ y) {
   nvae::pdl_enter();
   __shared__ float part[kSeThreads * 4];
-  __shared__ float spool[kSeMaxC];
+  __shared__ __align__(16) float spool[kSeMaxC];
   __shared__ float shid[kSeMaxHid];
   const int b = blockIdx.x, C4 = C >> 2, tid = threadIdx.x;
   const int G = kSeThreads / C4;  // row groups
@@ -63,7 +65,30 @@ __global__ void __launch_bounds__(kSeThreads) se_pool_gate_kernel(
   for (int c = tid; c < C; c += kSeThreads) {
     float s = b2[c];
     for (int j = 0; j < hid; ++j) s = fmaf(shid[j], __ldg(w2 + (int64_t)j * C + c), s);
-    gate[(int64_t)b * C + c] = 1.f / (1.f + expf(-s));
+    s = 1.f / (1.f + expf(-s));
+    gate[(int64_t)b * C + c] = s;
+    spool[c] = s;  // (the pooled values are no longer needed)
+  }
+  if (y == nullptr) return;
+  // fused residual merge for small samples: y = alpha*xres + beta*t'*gate -- the sample's t was just streamed by this
+  // CTA (L1/L2 hits), and one launch disappears
+  __syncthreads();
+  const float* xb = xres + (int64_t)b * HW * C;
+  float* yb = y + (int64_t)b * HW * C;
+  const int n4 = HW * C4;
+  for (int i = tid; i < n4; i += kSeThreads) {
+    const int k4 = i % C4;
+    float4 v = ldg4(tb + (int64_t)i * 4);
+    if (stat != nullptr) {
+      const float4 sc = ldg4(stat + 2 * C + k4 * 4), sh = ldg4(stat + 3 * C + k4 * 4);
+      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    }
+    const float4 g = *reinterpret_cast<const float4*>(&spool[k4 * 4]);
+    const float4 xr = ldg4(xb + (int64_t)i * 4);
+    float4 o;
+    o.x = fmaf(alpha, xr.x, beta * v.x * g.x); o.y = fmaf(alpha, xr.y, beta * v.y * g.y);
+    o.z = fmaf(alpha, xr.z, beta * v.z * g.z); o.w = fmaf(alpha, xr.w, beta * v.w * g.w);
+    stg4(yb + (int64_t)i * 4, o);
   }
 }
 
@@ -96,10 +121,10 @@ __global__ void __launch_bounds__(kSeThreads) se_bwd_gate_kernel(
     const float* __restrict__ dy, const float* __restrict__ t, const float* __restrict__ stat, int HW, int C, int hid,
     const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ hidden,
     const float* __restrict__ gate, float beta, float* __restrict__ dz2, float* __restrict__ dh,
-    float* __restrict__ dpool) {
+    float* __restrict__ dpool, float alpha, float* __restrict__ dt, float* __restrict__ dxres, int dxres_accumulate) {
   nvae::pdl_enter();
   __shared__ float part[kSeThreads * 4];
-  __shared__ float sdz[kSeMaxC];
+  __shared__ __align__(16) float sdz[kSeMaxC];
   __shared__ float sdh[kSeMaxHid];
   const int b = blockIdx.x, C4 = C >> 2, tid = threadIdx.x;
   const int G = kSeThreads / C4;
@@ -143,10 +168,37 @@ __global__ void __launch_bounds__(kSeThreads) se_bwd_gate_kernel(
     }
   }
   __syncthreads();
+  __syncthreads();  // (sdz is reused below: everyone is done reading it)
   for (int c = tid; c < C; c += kSeThreads) {
     float s = 0.f;
     for (int j = 0; j < hid; ++j) s = fmaf(sdh[j], __ldg(w1 + (int64_t)c * hid + j), s);
     dpool[(int64_t)b * C + c] = s;
+    sdz[c] = s;
+  }
+  if (dt == nullptr) return;
+  // fused apply for small samples: dt' = beta*dy*gate + dpool/HW ; dxres (+)= alpha*dy
+  __syncthreads();
+  const float inv_hw = 1.f / (float)HW;
+  const float* gb = gate + (int64_t)b * C;
+  float* dtb = dt + (int64_t)b * HW * C;
+  float* dxb = dxres != nullptr ? dxres + (int64_t)b * HW * C : nullptr;
+  const int n4 = HW * C4;
+  for (int i = tid; i < n4; i += kSeThreads) {
+    const int k4 = i % C4;
+    const float4 d = ldg4(db + (int64_t)i * 4), g = ldg4(gb + k4 * 4);
+    const float4 p = *reinterpret_cast<const float4*>(&sdz[k4 * 4]);
+    float4 o;
+    o.x = fmaf(beta * d.x, g.x, p.x * inv_hw); o.y = fmaf(beta * d.y, g.y, p.y * inv_hw);
+    o.z = fmaf(beta * d.z, g.z, p.z * inv_hw); o.w = fmaf(beta * d.w, g.w, p.w * inv_hw);
+    stg4(dtb + (int64_t)i * 4, o);
+    if (dxb != nullptr) {
+      float4 r = make_float4(alpha * d.x, alpha * d.y, alpha * d.z, alpha * d.w);
+      if (dxres_accumulate) {
+        const float4 e = *reinterpret_cast<const float4*>(dxb + (int64_t)i * 4);
+        r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+      }
+      stg4(dxb + (int64_t)i * 4, r);
+    }
   }
 }
 
@@ -259,8 +311,13 @@ extern "C" int nvae_se_fwd(const float* t, const float* stat, const float* xres,
   int rc = se_check(B, HW, C, hid);
   if (rc) return rc;
   if (!t || !xres || !w1 || !b1 || !w2 || !b2 || !pooled || !hidden || !gate || !y) return NVAE_E_NULLPTR;
-  nvae::launch(se_pool_gate_kernel, B, kSeThreads, 0, stream, t, stat, HW, C, hid, w1, b1, w2, b2, pooled, hidden, gate);
+  // one CTA per sample also merges the residual when a sample is small (<= 64 KB): at the model's 4x4 / 8x8 / 16x16
+  // scales that is one launch instead of two and the second read of t never leaves the SM's cache
+  const bool fuse = (size_t)HW * C * sizeof(float) <= kSeFuseBytes;
+  nvae::launch(se_pool_gate_kernel, B, kSeThreads, 0, stream, t, stat, HW, C, hid, w1, b1, w2, b2, pooled, hidden, gate, xres,
+               alpha, beta, fuse ? y : (float*)nullptr);
   NVAE_RETURN_IF_LAUNCH_FAILED();
+  if (fuse) return NVAE_OK;
   const int64_t n4 = (int64_t)B * HW * (C / 4);
   nvae::launch(se_apply_kernel, se_grid(n4, 256), 256, 0, stream, t, stat, xres, gate, n4, C / 4, (int64_t)HW * (C / 4), alpha,
                                                         beta, y);
@@ -283,11 +340,14 @@ extern "C" int nvae_se_bwd(const float* dy, const float* t, const float* stat, i
   float* dz2 = reinterpret_cast<float*>(ws);
   float* dpool = dz2 + (size_t)B * C;
   float* dh = dpool + (size_t)B * C;
-  nvae::launch(se_bwd_gate_kernel, B, kSeThreads, 0, stream, dy, t, stat, HW, C, hid, w1, w2, hidden, gate, beta, dz2, dh, dpool);
+  const bool fuse = (size_t)HW * C * sizeof(float) <= kSeFuseBytes;
+  nvae::launch(se_bwd_gate_kernel, B, kSeThreads, 0, stream, dy, t, stat, HW, C, hid, w1, w2, hidden, gate, beta, dz2, dh, dpool,
+               alpha, fuse ? dt : (float*)nullptr, dxres, dxres_accumulate);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   const int total = 2 * C * hid + C + hid;
   nvae::launch(se_bwd_weights_kernel, (total * 8 + 127) / 128, 128, 0, stream, pooled, hidden, dz2, dh, B, C, hid, dw1, db1, dw2, db2);
   NVAE_RETURN_IF_LAUNCH_FAILED();
+  if (fuse) return NVAE_OK;
   const int64_t n4 = (int64_t)B * HW * (C / 4);
   nvae::launch(se_bwd_apply_kernel, se_grid(n4, 256), 256, 0, stream, dy, gate, dpool, n4, C / 4, (int64_t)HW * (C / 4),
                                                             1.f / (float)HW, alpha, beta, dt, dxres, dxres_accumulate);
