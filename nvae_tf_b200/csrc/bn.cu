@@ -122,18 +122,24 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restri
   if (training) {
     const double n = (double)rows;
     const double n_last = (double)(rows - (int64_t)(nsplit - 1) * rows_per_split), n_full = (double)rows_per_split;
-    double acc = 0;
-#pragma unroll 4
-    for (int s = lane; s < nsplit; s += 32)
-      acc += (s == nsplit - 1 ? n_last : n_full) * part[((int64_t)s * 2) * C + c];
-    const double mu = warp_sum(acc) / n;
-    acc = 0;
+    // ONE pass over the partials (they are fp64, so the textbook sum n_s*m_s^2 - n*mu^2 has bits to spare; the shifted
+    // per-CTA pivots keep m_s small): three plain sums, one shuffle tree each -- half the dependent L2 round trips of
+    // the mean-then-M2 formulation
+    double a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll 4
     for (int s = lane; s < nsplit; s += 32) {
-      const double d = part[((int64_t)s * 2) * C + c] - mu;
-      acc += part[((int64_t)s * 2 + 1) * C + c] + (s == nsplit - 1 ? n_last : n_full) * d * d;
+      const double ns = s == nsplit - 1 ? n_last : n_full;
+      const double m = part[((int64_t)s * 2) * C + c], q = part[((int64_t)s * 2 + 1) * C + c];
+      a0 += ns * m;
+      a1 += q;
+      a2 += ns * m * m;
     }
-    const double M2 = warp_sum(acc);
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    const double mu = a0 / n;
+    double M2 = a1 + a2 - n * mu * mu;
+    if (M2 < 0) M2 = 0;
     if (lane != 0) return;
     mean = (float)mu;
     var = (float)(M2 / n);
