@@ -21,9 +21,20 @@ static BnGeom bn_geom(int64_t rows, int C) {
   g.C4 = C / 4;
   int lc = 1;
   while (lc < g.C4 && lc < 32) lc <<= 1;
+  // channel lanes per CTA: a chunk width that does not divide C/4 leaves idle lanes in the last chunk (C = 192: 48 float4
+  // lanes as 32 + 16 -> a quarter of all threads idle); take the widest power of two >= 8 (128-byte row segments) with
+  // the fewest wasted lanes
+  if (lc > 8) {
+    int best = lc, best_waste = (int)(ceil_div(g.C4, lc) * lc) - g.C4;
+    for (int w = lc >> 1; w >= 8; w >>= 1) {
+      const int waste = (int)(ceil_div(g.C4, w) * w) - g.C4;
+      if (waste < best_waste) { best = w; best_waste = waste; }
+    }
+    lc = best;
+  }
   g.LC = lc;
   g.RW = 32 / lc;
-  g.nchunk = (int)ceil_div(g.C4, 32);
+  g.nchunk = (int)ceil_div(g.C4, lc);
   const int64_t rows_iter = (int64_t)kBnWarps * g.RW;
   int64_t want = ceil_div(4 * kNumSMs, g.nchunk);            // ~4 CTAs per SM in total
   int64_t cap = ceil_div(rows, rows_iter * 4);               // >= 4 iterations of work per CTA
@@ -74,7 +85,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float* __res
   __shared__ float sm[kBnWarps][32][8];
   const int C4 = C >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int RW = 32 / LC, rsub = lane / LC, cl = lane % LC;
-  const int c4 = blockIdx.x * 32 + cl;
+  const int c4 = blockIdx.x * LC + cl;
   const bool cvalid = c4 < C4;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
   const int64_t r1 = r0 + rows_per_split < rows ? r0 + rows_per_split : rows;
@@ -228,7 +239,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const float* 
   __shared__ float sm[kBnWarps][32][8];
   const int C4 = C >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int RW = 32 / LC, rsub = lane / LC, cl = lane % LC;
-  const int c4 = blockIdx.x * 32 + cl;
+  const int c4 = blockIdx.x * LC + cl;
   const bool cvalid = c4 < C4;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
   const int64_t r1 = r0 + rows_per_split < rows ? r0 + rows_per_split : rows;
