@@ -233,6 +233,11 @@ NVAE_API int nvae_conv2d_wgrad(const NvaeConvDesc* d, const float* x, const floa
 NVAE_API int nvae_round_tf32(float* p, int64_t n, nvae_stream_t stream);
 /* 1 when nvae_conv2d_{fwd,dgrad,wgrad} (which = 0,1,2) would run this descriptor on the tcgen05 path. */
 NVAE_API int nvae_conv2d_uses_tensor_cores(const NvaeConvDesc* d, int which);
+/* Launch plan of the tcgen05 path for this descriptor (pure host function, no device needed; returns 0 and zeros when the
+ * descriptor does not take that path).  out[16] = {1, BN (tile columns), M tiles, N tiles, k-units per tile, CTAs,
+ * raw ring stages, TMEM A slots, accumulators, 3xFP16 (0/1), accumulators per tile (nsub), two M tiles per CTA (dual),
+ * split-K fix-up launch (0/1), dynamic shared memory bytes, workspace bytes >> 10, batch chunks of backward-filter}. */
+NVAE_API int nvae_conv2d_plan_info(const NvaeConvDesc* d, int which, int32_t* out);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer + schedules.   Replaces: optimizers.Adamax + CosineDecay train.py:128-131,

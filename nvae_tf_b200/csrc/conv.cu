@@ -84,6 +84,13 @@ extern "C" int nvae_round_tf32(float* p, int64_t n, nvae_stream_t stream) {
   return nvae_round_tf32_inplace(p, n, stream);
 }
 
+extern "C" int nvae_conv2d_plan_info(const NvaeConvDesc* d, int which, int32_t* out) {
+  if (out == nullptr) return 0;
+  for (int i = 0; i < 16; ++i) out[i] = 0;
+  if (nvae_conv_check(d) != NVAE_OK || d->precision == NVAE_PREC_FP32 || which < 0 || which > 2) return 0;
+  return nvae_conv_tc_plan_info(d, which, out) ? 1 : 0;
+}
+
 extern "C" int nvae_conv2d_uses_tensor_cores(const NvaeConvDesc* d, int which) {
   if (nvae_conv_check(d) != NVAE_OK || d->precision == NVAE_PREC_FP32) return 0;
   return nvae_conv_tc_supported(d, which) ? 1 : 0;

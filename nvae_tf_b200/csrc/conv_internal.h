@@ -19,6 +19,7 @@ int nvae_conv2d_wgrad_simt(const NvaeConvDesc* d, const float* x, const float* x
 // tcgen05 / TMA backend (conv_tc.cu).  which: 0 fwd, 1 dgrad, 2 wgrad.
 bool nvae_conv_tc_supported(const NvaeConvDesc* d, int which);
 size_t nvae_conv_tc_ws_bytes(const NvaeConvDesc* d, int which);
+bool nvae_conv_tc_plan_info(const NvaeConvDesc* d, int which, int32_t* out);
 int nvae_conv2d_fwd_tc(const NvaeConvDesc* d, const float* x, const float* x2, const float* w_tr, const float* bias,
                        const float* residual, float* y, void* ws, size_t ws_bytes, cudaStream_t stream);
 int nvae_conv2d_dgrad_tc(const NvaeConvDesc* d, const float* dy, const float* w_rnd, float* dx, float* dx2,

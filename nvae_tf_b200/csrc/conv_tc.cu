@@ -1743,6 +1743,20 @@ bool nvae_conv_tc_supported(const NvaeConvDesc* d, int which) {
 
 static int wgrad_chunks(const NvaeConvDesc* d);
 
+bool nvae_conv_tc_plan_info(const NvaeConvDesc* d, int which, int32_t* out) {
+  Plan pl;
+  bool ok;
+  if (which == 2) ok = plan_wgrad(d, &pl);
+  else if (which == 1 && d->stride == 2) ok = common_ok(d, 1) && plan_gemm(d, 1, s2_dgrad_taps(d, 0, 0).n, &pl);
+  else ok = plan_gemm(d, which, d->R * d->S, &pl);
+  if (!ok) return false;
+  const int32_t v[16] = {1, pl.BN, pl.n_mtiles, pl.n_ntiles, pl.KU, pl.G, pl.stages, pl.lo_stages, pl.acc_bufs, pl.f16,
+                         pl.nsub, pl.dual, pl.split ? 1 : 0, (int32_t)pl.smem, (int32_t)(nvae_conv_tc_ws_bytes(d, which) >> 10),
+                         which == 2 ? wgrad_chunks(d) : 1};
+  for (int i = 0; i < 16; ++i) out[i] = v[i];
+  return true;
+}
+
 size_t nvae_conv_tc_ws_bytes(const NvaeConvDesc* d, int which) {
   Plan pl;
   if (which == 2) {
