@@ -267,6 +267,64 @@ def test_conv2d_tensor_core_modes(lib_built, case, mode, tol, monkeypatch):
         check("db", npy(conv.bias.grad), bo.grad.numpy(), tol)
 
 
+@pytest.mark.parametrize("shape", [(144, 16, 16, 384, 384), (144, 32, 32, 192, 192)])
+def test_conv2d_full_size_3xfp16_agrees_with_3xtf32(lib_built, shape, monkeypatch):
+    """BASELINE-size check of the dominant GEMMs (batch 144; the float64 oracle would need minutes per case): the 3xFP16
+    path the step uses for them (two accumulators / two M tiles per CTA, pixel-aligned split of the 226 MB filter
+    gradient) must agree with the independent 3xTF32 path on the same operands -- forward, backward-data and
+    backward-filter, each far inside the 1e-3 bound -- and 5x5 SAME convolution is linear: conv(2x, w) == 2 conv(x, w)
+    bit for bit (power-of-two scale: the absmax-derived operand scale moves by exactly one exponent)."""
+    import ctypes as C
+    from nvae_tf_b200 import _lib
+    from nvae_tf_b200 import runtime as R
+    from nvae_tf_b200.layers import Conv2D
+    N, Hh, W, Cin, Cout = shape
+    monkeypatch.delenv("NVAE_F16X3_MIN_GFLOP", raising=False)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    with R.Runtime(seed=7, precision=_lib.NVAE_PREC_TF32X3) as rt:
+        conv = Conv2D(Cout, (5, 5), padding="same", in_channels=Cin, name="c")
+        rt.finalize()
+        conv.kernel.assign((torch.randn(5, 5, Cin, Cout, generator=g) / np.sqrt(25 * Cin)).numpy())
+        conv.bias.assign(torch.zeros(Cout).numpy())
+        x = torch.randn(N, Hh, W, Cin, generator=g)
+        x = x * torch.rand(1, 1, 1, Cin, generator=g) * 30.0          # per-channel magnitudes spread over a decade+
+        dy = torch.randn(N, Hh, W, Cout, generator=g) * 1e-4
+        res = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("NVAE_F16X3", mode)
+            d = R.conv_desc(rt, tuple(x.shape), 0, conv.kernel.shape, 1)
+            info = (C.c_int32 * 16)()
+            rt.lib._nvae_conv2d_plan_info(C.byref(d), 0, info)
+            assert info[9] == int(mode)  # the arithmetic under test is the one that runs
+            xt = R.DeviceTensor(x.to(rt.device), True)
+            with rt.gradient_tape() as tape:
+                y = conv(xt)
+            y.grad = dy.to(rt.device)
+            rt.backward(tape)
+            torch.cuda.synchronize()
+            res[mode] = (y.data.double().cpu(), xt.grad.double().cpu(), torch.as_tensor(conv.kernel.grad).double().cpu().clone())
+            if mode == "1":
+                x2 = R.DeviceTensor((2.0 * x).to(rt.device), False)
+                y2 = conv(x2)
+                torch.cuda.synchronize()
+                assert torch.equal(y2.data.cpu(), 2.0 * y.data.cpu())
+        # the two arithmetics against each other (3xTF32 splits by truncation: its dropped terms are biased and add up
+        # over K = 9600; 3xFP16 rounds to nearest)
+        for name, a, b in zip(("y", "dx", "dw"), res["1"], res["0"]):
+            err = float((a - b).abs().max() / b.abs().max())
+            assert err <= 2e-4, f"{name}: 3xFP16 vs 3xTF32 max|d|/max|ref| = {err:.2e}"
+        # ... and both against the float64 oracle on the first image (forward and backward-data are per-sample).  At
+        # K = 9600 the floor is the tensor core's own fp32 accumulation over 1 800 - 3 600 chained MMAs (~3e-5 measured for
+        # either arithmetic), a factor 30 inside the 1e-3 bound
+        xo = x[:1].double().requires_grad_(True)
+        yo = O.conv2d(xo, torch.as_tensor(npy(conv.kernel.value)), None, 1)
+        yo.backward(dy[:1].double())
+        for mode, tol in (("1", 1e-4), ("0", 2e-4)):
+            ey = float((res[mode][0][:1] - yo.detach()).abs().max() / yo.detach().abs().max())
+            ex = float((res[mode][1][:1] - xo.grad).abs().max() / xo.grad.abs().max())
+            assert ey <= tol and ex <= tol, f"NVAE_F16X3={mode}: y {ey:.2e}, dx {ex:.2e} vs float64"
+
+
 def test_conv2d_concat_output_and_accumulating_dgrad(rt):
     """SkipScaler (preprocess.py:65-74): four strided 1x1 convs on shifted views write channel slices of one
     tensor; their dgrads accumulate into the shared input gradient."""
