@@ -19,6 +19,11 @@
 // has eight converter warps write the TF32-rounded remainders  lo = rn(v - trunc(v))  of every staged tile
 // to a second shared-memory ring, and issues three MMAs per K step: A_hi*B_hi as soon as the tile lands (the
 // converters run meanwhile), then A_hi*B_lo + A_lo*B_hi.  Nothing low-order ever touches HBM or L2.
+// The large GEMMs of that mode (>= 20 GFLOP per launch: the six 5x5 convolutions of the postprocess tower, 87 % of the
+// step's FLOPs) run the same three-term product as 3xFP16 on kind::f16 instead (TcParams::f16): operands scaled by a power
+// of two from their absmax, A split by the converters into packed fp16 pairs in TMEM, B (weights / dY) split ahead of
+// the launch into rows the SAME tensor maps stage, two accumulators per CTA sharing the staged tiles (nsub / dual) --
+// twice the MMA rate, half the shared-memory bytes per stage.  DESIGN.md 3.1b.
 // Scheduling: stream-K.  The (tile, k-unit) space is cut into gridDim.x equal contiguous ranges (one CTA per
 // SM, at most 148), so every SM gets the same number of pipeline stages whatever the tile count; a CTA
 // that covers only part of a tile's K range writes its raw accumulator to a partial buffer and a fix-up

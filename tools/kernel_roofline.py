@@ -3,7 +3,8 @@
 micro-benchmark of BASELINE configs[1] (NHWC batch 256 at 14x14x64 and 7x7x128, plus the model's own shapes).
 
 Bandwidth-bound kernels are timed on tensors larger than the 126 MB L2 (or with an L2 flush between repetitions)
-with CUDA events on the launching stream; achieved = ALGORITHMIC bytes (every logically required
+with CUDA events around the replay of a one-call CUDA graph (the step replays the same launches from a graph, so the CPU
+launch gaps between the two or three kernels of an operator are not part of it); achieved = ALGORITHMIC bytes (every logically required
 tensor read/written once) / time; peak = MEASURED_PEAKS.json hbm_gbs.
 usage (GPU box): python tools/kernel_roofline.py > gpurun_out/kernel_roofline.md
 """
@@ -66,6 +67,20 @@ def graph_timed(fn, iters=10):
     return timed(g.replay, reps=7, flush=False) / iters
 
 
+def timed_op(fn, reps=5):
+    """One call of a (possibly multi-launch) operator, captured into a CUDA graph so that the CPU launch overhead between
+    its kernels does not count -- the training step replays these same launches from a graph -- and replayed with the L2
+    flushed before every repetition."""
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.graph(g, stream=s):
+        fn()
+    return timed(g.replay, reps=reps, flush=True)
+
+
 def row(name, shape, nbytes, us):
     gbs = nbytes / us / 1e3
     print(f"| `{name}` | {shape} | {nbytes / 1e6:.1f} | {us:.1f} | {gbs:.0f} | {100 * gbs / HBM:.0f}% |")
@@ -94,22 +109,22 @@ def membound():
             stat = torch.empty(4, Cc, device="cuda")
             ws, wsb = rt.workspace(max(lib._nvae_bn_ws_bytes(rows, Cc), lib._nvae_dwconv5x5_bwd_filter_ws_bytes(N, H, W, Cc)))
             tag = f"[{N},{H},{W},{Cc}]"
-            us = timed(lambda: lib.bn_stats(x.data_ptr(), rows, Cc, bn.gamma.ptr(), bn.beta.ptr(), bn.moving_mean.ptr(),
+            us = timed_op(lambda: lib.bn_stats(x.data_ptr(), rows, Cc, bn.gamma.ptr(), bn.beta.ptr(), bn.moving_mean.ptr(),
                                             bn.moving_variance.ptr(), 1, 0.05, 1e-5, stat.data_ptr(), ws, wsb, rt.stream))
             row("bn_stats + bn_finalize", tag, 4 * n, us)
-            us = timed(lambda: lib.bn_act_fwd(x.data_ptr(), rows, Cc, stat.data_ptr(), 1, 0, 0, 0, y.data_ptr(), rt.stream))
+            us = timed_op(lambda: lib.bn_act_fwd(x.data_ptr(), rows, Cc, stat.data_ptr(), 1, 0, 0, 0, y.data_ptr(), rt.stream))
             row("bn_act_fwd (BN-apply + swish)", tag, 8 * n, us)
-            us = timed(lambda: lib.bn_act_bwd(dy.data_ptr(), x.data_ptr(), rows, Cc, stat.data_ptr(), 1, 0, 0, 1, None, 0.0,
+            us = timed_op(lambda: lib.bn_act_bwd(dy.data_ptr(), x.data_ptr(), rows, Cc, stat.data_ptr(), 1, 0, 0, 1, None, 0.0,
                                               0, dx.data_ptr(), bn.gamma.gptr(), bn.beta.gptr(), ws, wsb, rt.stream))
             row("bn_act_bwd (reduce + finalize + apply)", tag, 20 * n, us)
             if H <= 14:
-                us = timed(lambda: lib.dwconv5x5_fwd(x.data_ptr(), stat.data_ptr(), 1, N, H, W, Cc, dw.depthwise_kernel.ptr(),
+                us = timed_op(lambda: lib.dwconv5x5_fwd(x.data_ptr(), stat.data_ptr(), 1, N, H, W, Cc, dw.depthwise_kernel.ptr(),
                                                      dw.bias.ptr(), y.data_ptr(), rt.stream))
                 row("dwconv5x5_fwd (+BN-apply+swish on load)", tag, 8 * n, us)
-                us = timed(lambda: lib.dwconv5x5_bwd_data(dy.data_ptr(), N, H, W, Cc, dw.depthwise_kernel.ptr(),
+                us = timed_op(lambda: lib.dwconv5x5_bwd_data(dy.data_ptr(), N, H, W, Cc, dw.depthwise_kernel.ptr(),
                                                           dx.data_ptr(), rt.stream))
                 row("dwconv5x5_bwd_data", tag, 8 * n, us)
-                us = timed(lambda: lib.dwconv5x5_bwd_filter(x.data_ptr(), stat.data_ptr(), 1, dy.data_ptr(), N, H, W, Cc,
+                us = timed_op(lambda: lib.dwconv5x5_bwd_filter(x.data_ptr(), stat.data_ptr(), 1, dy.data_ptr(), N, H, W, Cc,
                                                             dw.depthwise_kernel.gptr(), dw.bias.gptr(), ws, wsb, rt.stream))
                 row("dwconv5x5_bwd_filter", tag, 8 * n, us)
             del x, y, dy, dx
@@ -146,11 +161,11 @@ def membound():
             pooled, hidden, gate = torch.empty(N, Cc, device="cuda"), torch.empty(N, hid, device="cuda"), torch.empty(N, Cc, device="cuda")
             ws, wsb = rt.workspace(lib._nvae_se_bwd_ws_bytes(N, Cc, hid))
             tag = f"[{N},{H},{W},{Cc}]"
-            us = timed(lambda: lib.se_fwd(t.data_ptr(), None, xr.data_ptr(), N, H * W, Cc, hid, se.dense1.kernel.ptr(),
+            us = timed_op(lambda: lib.se_fwd(t.data_ptr(), None, xr.data_ptr(), N, H * W, Cc, hid, se.dense1.kernel.ptr(),
                                           se.dense1.bias.ptr(), se.dense2.kernel.ptr(), se.dense2.bias.ptr(), 0.1, 1.0,
                                           pooled.data_ptr(), hidden.data_ptr(), gate.data_ptr(), y.data_ptr(), rt.stream))
             row("se_fwd (pool, FCs, scale + residual)", tag, 12 * n, us)
-            us = timed(lambda: lib.se_bwd(dy.data_ptr(), t.data_ptr(), None, N, H * W, Cc, hid, se.dense1.kernel.ptr(),
+            us = timed_op(lambda: lib.se_bwd(dy.data_ptr(), t.data_ptr(), None, N, H * W, Cc, hid, se.dense1.kernel.ptr(),
                                           se.dense2.kernel.ptr(), pooled.data_ptr(), hidden.data_ptr(), gate.data_ptr(), 0.1,
                                           1.0, dt.data_ptr(), dxr.data_ptr(), 0, se.dense1.kernel.gptr(),
                                           se.dense1.bias.gptr(), se.dense2.kernel.gptr(), se.dense2.bias.gptr(), ws, wsb,
@@ -164,18 +179,18 @@ def membound():
         eps = torch.randn(B, HW, L, device="cuda")
         z, kl = torch.empty(B, HW, L, device="cuda"), torch.empty(B, device="cuda")
         dist = torch.empty(4, B, HW, L, device="cuda")
-        us = timed(lambda: lib.latent_fwd(enc.data_ptr(), dec.data_ptr(), eps.data_ptr(), B, HW, L, z.data_ptr(), kl.data_ptr(),
+        us = timed_op(lambda: lib.latent_fwd(enc.data_ptr(), dec.data_ptr(), eps.data_ptr(), B, HW, L, z.data_ptr(), kl.data_ptr(),
                                           None, None, dist.data_ptr(), rt.stream))
         row("latent_fwd (params, sample, KL, dist)", f"[{B},8,8,20]", 4 * B * HW * L * (2 + 2 + 1 + 1 + 4), us)
         dz, klw = torch.randn_like(z), torch.full((1,), 0.01, device="cuda")
         de, dd = torch.empty_like(enc), torch.empty_like(dec)
-        us = timed(lambda: lib.latent_bwd(enc.data_ptr(), dec.data_ptr(), eps.data_ptr(), dz.data_ptr(), klw.data_ptr(), B, HW,
+        us = timed_op(lambda: lib.latent_bwd(enc.data_ptr(), dec.data_ptr(), eps.data_ptr(), dz.data_ptr(), klw.data_ptr(), B, HW,
                                           L, de.data_ptr(), dd.data_ptr(), rt.stream))
         row("latent_bwd", f"[{B},8,8,20]", 4 * B * HW * L * (2 + 2 + 1 + 1 + 2 + 2), us)
         n = 40_128_896
         pbuf, g, m, v = (torch.randn(n, device="cuda") for _ in range(4))
         hyper = torch.tensor([0.5, 1e-3, 1e-3, 1, 0, 0, 0, 0], device="cuda")
-        us = timed(lambda: lib.adamax(pbuf.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, hyper.data_ptr(), 0.9,
+        us = timed_op(lambda: lib.adamax(pbuf.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, hyper.data_ptr(), 0.9,
                                       0.999, 1e-7, 1.0, rt.stream))
         row("adamax (whole parameter arena)", "[40.1M]", 28 * n, us)
         fused = os.environ.get("NVAE_BN_FUSED", "1") != "0"
