@@ -59,6 +59,14 @@ NVAE_API int nvae_version(void);
  * count once, at capture).  bench.py derives `gpu_launches` from it. */
 NVAE_API uint64_t nvae_launch_count(void);
 NVAE_API const char* nvae_build_info(void);
+/* CUDA-graph plumbing for the host side (the step is captured by the caller's framework; these only instantiate and
+ * launch it): instantiate a captured cudaGraph_t so that the per-node priorities recorded at capture -- main chain on a
+ * high-priority stream, weight-gradient side stream at normal priority -- are honoured by the CTA scheduler
+ * (cudaGraphInstantiateFlagUseNodePriority; a plain instantiation runs every node at the launch stream's priority).
+ * `graph` = cudaGraph_t, `*exec` = cudaGraphExec_t.  Return 0 or a cudaError_t. */
+NVAE_API int nvae_graph_instantiate(void* graph, int use_node_priority, void** exec);
+NVAE_API int nvae_graph_launch(void* exec, nvae_stream_t stream);
+NVAE_API int nvae_graph_destroy(void* exec);
 
 /* ------------------------------------------------------------------------------------------
  * BatchNormalization(momentum=0.05, epsilon=1e-5)      Replaces: common.py:148,166;

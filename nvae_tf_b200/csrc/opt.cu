@@ -142,6 +142,22 @@ using namespace nvae;
 unsigned long long nvae_launch_counter = 0;
 extern "C" uint64_t nvae_launch_count(void) { return (uint64_t)nvae_launch_counter; }
 extern "C" int nvae_version(void) { return 100; }
+
+extern "C" int nvae_graph_instantiate(void* graph, int use_node_priority, void** exec) {
+  if (graph == nullptr || exec == nullptr) return NVAE_E_NULLPTR;
+  cudaGraphExec_t e = nullptr;
+  const cudaError_t rc = cudaGraphInstantiateWithFlags(&e, reinterpret_cast<cudaGraph_t>(graph),
+                                                       use_node_priority ? cudaGraphInstantiateFlagUseNodePriority : 0);
+  *exec = e;
+  return (int)rc;
+}
+extern "C" int nvae_graph_launch(void* exec, nvae_stream_t stream) {
+  if (exec == nullptr) return NVAE_E_NULLPTR;
+  return (int)cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(exec), stream);
+}
+extern "C" int nvae_graph_destroy(void* exec) {
+  return exec == nullptr ? NVAE_OK : (int)cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(exec));
+}
 extern "C" const char* nvae_build_info(void) { return "libnvae_b200 sm_100a (tcgen05/TMA) built " __DATE__ " " __TIME__; }
 
 extern "C" int nvae_schedule_step(int64_t* counters, float* hyper, float warmup_iters, float lr0, float decay_steps,
