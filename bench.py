@@ -212,9 +212,9 @@ def main():
     from nvae_tf_b200 import _lib, parallel
     from nvae_tf_b200.models import NVAE, Adamax, CosineDecay
 
-    # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (printed to stdout at NCCL_DEBUG=VERSION) off it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 prints ONE JSON line on stdout: NCCL's version banner / warnings (stdout at NCCL_DEBUG=VERSION or WARN, which
+    # this image sets) go to stderr instead
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     world = parallel.init_from_env()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
