@@ -1,0 +1,120 @@
+"""TensorFlow side of the drop-in: `tf.custom_gradient` wrappers over the custom ops of tf_op/nvae_ops.cc, shaped so
+that the reference's layers (common.py, encoder.py, decoder.py) call them where they call Keras layers today and
+`tf.GradientTape` in `NVAE.train_step` (models.py:116-127) works unchanged.
+
+Needs TensorFlow (the reference pins 2.3) and `make -C tf_op` at the user's site; this repository's build image has
+neither, so this module is shipped as source (byte-compiled by tests/test_tf_op_source.py) and the kernels it reaches are
+tested through the same C ABI with ctypes (tests/test_kernels_gpu.py, tests/test_model_gpu.py).
+
+Activation codes (include/nvae_b200.h): 0 none, 1 swish, 2 ELU.  Precision 2 = NVAE_PREC_TF32X3 (fp32-grade products).
+"""
+import os
+
+import tensorflow as tf
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ops = tf.load_op_library(os.path.join(_HERE, "libnvae_tf_ops.so"))
+_EMPTY = tf.zeros([0], tf.float32)
+
+
+def conv2d(x, kernel, kernel_tr, bias, stride=1, x2=None, residual=None, precision=2):
+    """SpectralNormalization(Conv2D(padding="same"))(concat(x, x2)) (+ residual).  `kernel` is the (already normalised)
+    HWIO variable, `kernel_tr` its transposed operand copy written by the once-per-step nvae_spectral_norm pass."""
+    x2_ = _EMPTY if x2 is None else x2
+    res_ = _EMPTY if residual is None else residual
+
+    @tf.custom_gradient
+    def f(x, x2_, kernel, bias, res_):
+        y = _ops.nvae_conv2d_fwd(x=x, x2=x2_, w=kernel, w_tr=kernel_tr, bias=bias, residual=res_, stride=stride,
+                                 precision=precision)
+
+        def grad(dy):
+            dx, dx2 = _ops.nvae_conv2d_dgrad(dy=dy, w=kernel, w_rnd=kernel, in_h=x.shape[1], in_w=x.shape[2],
+                                             cin=x.shape[3], cin2=0 if x2 is None else x2.shape[3], stride=stride,
+                                             precision=precision)
+            dw, db = _ops.nvae_conv2d_wgrad(x=x, x2=x2_, dy=dy, r=kernel.shape[0], s=kernel.shape[1], stride=stride,
+                                            precision=precision)
+            # straight-through to the normalised kernel variable (tfa.SpectralNormalization semantics)
+            return dx, (None if x2 is None else dx2), dw, db, (None if residual is None else dy)
+        return y, grad
+    return f(x, x2_, kernel, bias, res_)
+
+
+def bn_act(x, bn, act=1, training=True, upsample=False):
+    """activation(BatchNormalization(momentum=0.05, epsilon=1e-5)(x)) [-> tf.image.resize nearest x2]: common.py:165-172,
+    encoder.py:102-104, decoder.py:139,143.  `bn` is the Keras layer (gamma, beta, moving_mean, moving_variance)."""
+    @tf.custom_gradient
+    def f(x, gamma, beta):
+        out, stat = _ops.nvae_bn_fwd(x=x, gamma=gamma, beta=beta, moving_mean=bn.moving_mean,
+                                     moving_var=bn.moving_variance, training=training, momentum=bn.momentum,
+                                     epsilon=bn.epsilon, act=act, upsample=upsample)
+
+        def grad(dout):
+            return _ops.nvae_bn_act_bwd(dout=dout, x=x, stat=stat, training=training, act=act, upsample=upsample)
+        return out, grad
+    return f(x, bn.gamma, bn.beta)
+
+
+def bn_stat(x, bn, training=True):
+    """Only the [4, C] statistics block (mean, invstd, scale, shift) for consumers that fuse the BN-apply into their own
+    load (depthwise conv, squeeze-excitation).  The gradient flows through those consumers' `da` / `dt` and
+    nvae_bn_act_bwd (see dwconv_bn_act)."""
+    _, stat = _ops.nvae_bn_fwd(x=x, gamma=bn.gamma, beta=bn.beta, moving_mean=bn.moving_mean, moving_var=bn.moving_variance,
+                               training=training, momentum=bn.momentum, epsilon=bn.epsilon, act=0, upsample=False)
+    return tf.stop_gradient(stat)
+
+
+def dwconv_bn_act(x, bn, depthwise_kernel, bias, act=1, training=True):
+    """DepthwiseConv2D((5, 5), padding="same")(swish(BN(x))) with the BN-apply + activation fused into the load
+    (decoder.py:130,141-142)."""
+    @tf.custom_gradient
+    def f(x, gamma, beta, w, b):
+        stat = bn_stat(x, bn, training)
+        y = _ops.nvae_dwconv5x5_fwd(x=x, stat=stat, w=w, bias=b, act=act)
+
+        def grad(dy):
+            da, dw, db = _ops.nvae_dwconv5x5_bwd(x=x, stat=stat, w=w, dy=dy, act=act)
+            dx, dgamma, dbeta = _ops.nvae_bn_act_bwd(dout=da, x=x, stat=stat, training=training, act=act, upsample=False)
+            return dx, dgamma, dbeta, dw, db
+        return y, grad
+    return f(x, bn.gamma, bn.beta, depthwise_kernel, bias)
+
+
+def se_residual(t, xres, se, alpha=0.1, beta=1.0, bn=None, training=True):
+    """alpha * xres + beta * SqueezeExcitation(BN(t)) (bn optional): common.py:129-142 with the cell tails encoder.py:107,
+    decoder.py:147 (alpha=0.1, beta=1) and preprocess.py:107, postprocess.py:58 (alpha=1, beta=0.1)."""
+    w1, b1, w2, b2 = se.dense1.kernel, se.dense1.bias, se.dense2.kernel, se.dense2.bias
+    gamma = _EMPTY if bn is None else bn.gamma
+    beta_ = _EMPTY if bn is None else bn.beta
+
+    @tf.custom_gradient
+    def f(t, xres, w1, b1, w2, b2, gamma, beta_):
+        stat = _EMPTY if bn is None else bn_stat(t, bn, training)
+        y, pooled, hidden, gate = _ops.nvae_se_fwd(t=t, stat=stat, xres=xres, w1=w1, b1=b1, w2=w2, b2=b2, alpha=alpha,
+                                                   beta=beta)
+
+        def grad(dy, *_unused):
+            dt, dxres, dw1, db1, dw2, db2 = _ops.nvae_se_bwd(dy=dy, t=t, stat=stat, w1=w1, w2=w2, pooled=pooled,
+                                                             hidden=hidden, gate=gate, alpha=alpha, beta=beta)
+            if bn is None:
+                return dt, dxres, dw1, db1, dw2, db2, None, None
+            dx, dgamma, dbeta = _ops.nvae_bn_act_bwd(dout=dt, x=t, stat=stat, training=training, act=0, upsample=False)
+            return dx, dxres, dw1, db1, dw2, db2, dgamma, dbeta
+        return y, grad
+    return f(t, xres, w1, b1, w2, b2, gamma, beta_)
+
+
+def latent(enc_p, dec_p, eps, kl_weight):
+    """Sampler.call (common.py:76-102): returns (z, kl[B], dist[4, B, HW, L]).  `dec_p=None` is the z_idx == 0 branch.
+    `kl_weight` (one float: beta * balance coefficient / B, models.py:204-222) scales the KL term's gradient."""
+    dec_ = _EMPTY if dec_p is None else dec_p
+
+    @tf.custom_gradient
+    def f(enc_p, dec_):
+        z, kl, dist = _ops.nvae_latent_fwd(enc_p=enc_p, dec_p=dec_, eps=eps)
+
+        def grad(dz, dkl, ddist):
+            d_enc, d_dec = _ops.nvae_latent_bwd(enc_p=enc_p, dec_p=dec_, eps=eps, dz=dz, kl_weight=kl_weight)
+            return d_enc, (None if dec_p is None else d_dec)
+        return (z, kl, dist), grad
+    return f(enc_p, dec_)
