@@ -38,21 +38,33 @@ BATCH = 144
 FLOP_PER_IMAGE = 38.87e9  # 6 x 6.478 GMAC: fwd + dgrad + wgrad
 
 
-def default_cfg():
-    from oracle import nvae_oracle as O  # config dataclass only; the oracle is never on the GPU path
-    return O.NVAEConfig()
+# BASELINE configs: "mnist" = configs[2] (the metric's config); "cifar" = configs[4], 32x32x3 with a deeper hierarchy
+# (three latent scales 8x8 / 4x4 / 2x2, groups [5,10,20] = 35, 215 M parameters; the head keeps the reference's single output
+# channel, postprocess.py:29 -- logits broadcast over the 3 input channels, README.md:25-27)
+CONFIGS = {
+    "mnist": dict(groups=[5, 10], channels=1, flop_per_image=38.87e9,
+                  workload="full MNIST-config NVAE train step (train.py defaults: 40.1M params, 15 latent groups, "
+                           "KL+recon+BN-gamma loss, SN, Adamax), BASELINE configs[2]"),
+    "cifar": dict(groups=[5, 10, 20], channels=3, flop_per_image=6 * 7.20e9,
+                  workload="CIFAR-10-shape 32x32x3 synthetic NVAE train step, groups [5,10,20] (35 latent groups, 3 scales, "
+                           "215M params), BASELINE configs[4]"),
+}
 
 
-def mirror_kwargs(batch):
+def mirror_kwargs(batch, config="mnist"):
+    c = CONFIGS[config]
     return dict(n_encoder_channels=32, n_decoder_channels=32, res_cells_per_group=1, n_preprocess_blocks=2,
-                n_preprocess_cells=3, n_latent_per_group=20, n_latent_scales=2, n_groups_per_scale=[5, 10],
-                n_postprocess_blocks=2, n_post_process_cells=3, sr_lambda=0.01, scale_factor=2, total_epochs=400,
-                n_total_iterations=417 * 400, step_based_warmup=True, input_shape=[batch, 32, 32, 1])
+                n_preprocess_cells=3, n_latent_per_group=20, n_latent_scales=len(c["groups"]),
+                n_groups_per_scale=list(c["groups"]), n_postprocess_blocks=2, n_post_process_cells=3, sr_lambda=0.01,
+                scale_factor=2, total_epochs=400, n_total_iterations=417 * 400, step_based_warmup=True,
+                input_shape=[batch, 32, 32, c["channels"]])
 
 
-def synthetic_images(batch, seed):
+def synthetic_images(batch, seed, config="mnist"):
     import numpy as np
     rng = np.random.default_rng(seed)
+    if config == "cifar":
+        return (rng.random((batch, 32, 32, 3)) < 0.13).astype(np.float32)
     x = (rng.random((batch, 28, 28, 1)) < 0.13).astype(np.float32)
     return np.pad(x, ((0, 0), (2, 2), (2, 2), (0, 0)))
 
@@ -94,6 +106,9 @@ class ClockSampler:
 # CPU arm: the oracle port of the reference's algorithm (TensorFlow itself is not installable here)
 # ------------------------------------------------------------------------------------------
 def cpu_step_fn(batch, threads):
+    """One FULL train step of the oracle port in torch-CPU fp32: forward, losses, autograd backward over all 666
+    trainable tensors, Adamax + CosineDecay update, SN / BN moving-statistics write-back -- the same work the GPU arm's
+    step does (train.py defaults, batch `batch`)."""
     import numpy as np
     import torch
     import helpers as H  # noqa: F401
@@ -104,15 +119,24 @@ def cpu_step_fn(batch, threads):
     pt = O.to_torch(params, trainable, dtype=torch.float32)
     x = torch.as_tensor(synthetic_images(batch, 1))
     eps = [e.float() for e in O.make_eps(s, batch, seed=1)]
+    slots = {n: (torch.zeros_like(pt[n]), torch.zeros_like(pt[n])) for n in trainable}
 
     def step(i):
         out, c = O.train_step_loss(cfg, s, pt, bnl, x, eps, steps=20000 + i, training=True)
-        O.grads_wrt_trainables(out["loss"], c, trainable)
+        grads = O.grads_wrt_trainables(out["loss"], c, trainable)
+        with torch.no_grad():
+            for n, v in c.new_stats.items():  # in-place W/sigma, u, moving statistics
+                pt[n] = v.detach().requires_grad_(pt[n].requires_grad)
+            lr = O.cosine_decay_lr(i, 400 * 417)
+            for n in trainable:
+                p, m, v = O.adamax_update(pt[n].detach(), grads[n], slots[n][0], slots[n][1], i + 1, lr)
+                pt[n] = p.requires_grad_(True)
+                slots[n] = (m, v)
         return float(out["loss"].detach())
     return step
 
 
-def cpu_baseline(sample_batch, budget_s=12.0):
+def cpu_baseline(sample_batch, budget_s=20.0):
     threads = os.cpu_count() or 1
     step = cpu_step_fn(sample_batch, threads)
     step(0)  # warm-up (thread pools, oneDNN primitive caches)
@@ -122,9 +146,10 @@ def cpu_baseline(sample_batch, budget_s=12.0):
         step(n)
     dt = time.perf_counter() - t0
     return {"value": n * sample_batch / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"1 warm-up + {n} timed full train steps (fwd+bwd, no optimizer) of the oracle port in torch-CPU "
-                      f"fp32 at batch {sample_batch} of the same config (~{budget_s:.0f} s of CPU work); TensorFlow (the "
-                      f"reference's runtime) is not installable in this image", "seconds": dt}
+            "sample": f"1 warm-up + {n} timed full train steps (fwd + bwd + Adamax) of the oracle port in torch-CPU "
+                      f"fp32 at batch {sample_batch} of the same config (~{dt:.0f} s of CPU work); TensorFlow (the "
+                      f"reference's runtime) is not installable in this image", "seconds": dt,
+            "same_config": sample_batch == BATCH}
 
 
 def run_reference(args):
@@ -134,20 +159,36 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     sample = args.cpu_batch
     step = cpu_step_fn(sample, threads)
-    for i in range(args.warmup):
-        step(i)
+    t0 = time.perf_counter()
+    step(0)
+    step(1)
+    per = (time.perf_counter() - t0) / 2
+    # bound the whole run to a few minutes: when a batch-144 step is too slow on this host, shrink the per-step sample
+    budget = 240.0
+    while per * (args.steps + args.warmup) > budget and sample > 16:
+        per *= 0.5
+        sample = max(16, sample // 2)
+        step = None
+    if step is None:
+        step = cpu_step_fn(sample, threads)
+        step(0)
+    for i in range(max(args.warmup - 2, 0)):
+        step(2 + i)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        step(i)
+        step(args.warmup + i)
     dt = time.perf_counter() - t0
     v = sample * args.steps / dt
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "full MNIST-config NVAE train step (train.py defaults, 40.1M params)",
-                       "batch_per_step": sample, "note": "bounded CPU sample of the batch-144 workload"},
+            "config": {"workload": CONFIGS["mnist"]["workload"], "batch_per_gpu": sample, "batch_per_step": sample,
+                       "same_config": sample == BATCH,
+                       "note": "the reference's algorithm (oracle port, torch-CPU fp32, all host threads): full step incl. "
+                               "Adamax; TensorFlow itself is not installable in this image"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} timed steps at batch {sample}, oracle port, torch-CPU fp32"},
+                             "sample": f"{args.steps} timed full train steps (fwd + bwd + Adamax) at batch {sample}, "
+                                       f"oracle port, torch-CPU fp32"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -156,8 +197,23 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # roofline of the dominant kernel, measured live
 # ------------------------------------------------------------------------------------------
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant 3xFP16 launch (profiles/r01i_ncu_conv_f16_5x5_384.md)
-DOMINANT_TRAFFIC_F16 = 104.1e6
+def dominant_traffic(f16, x3):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch from the committed `ncu --set full` summary
+    (profiles/dominant_kernel_traffic.json), valid only for the conv_tc.cu revision it was captured from: when the
+    kernel source changed since, the reading is stale and `traffic` is reported as null."""
+    import hashlib
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+        src = open(os.path.join(ROOT, "nvae_tf_b200", "csrc", "conv_tc.cu"), "rb").read()
+    except OSError:
+        return None, "profiles/dominant_kernel_traffic.json missing"
+    key = "f16x3" if f16 else ("tf32x3" if x3 else None)
+    ent = rec.get(key) if key else None
+    if ent is None:
+        return None, "no capture for this arithmetic"
+    if ent.get("conv_tc_sha16") != hashlib.sha256(src).hexdigest()[:16]:
+        return None, f"stale: {ent.get('source')} was captured from another revision of conv_tc.cu"
+    return float(ent["dram_bytes"]), ent.get("source")
 
 
 def measure_dominant_kernel(model, reps=5):
@@ -190,6 +246,79 @@ def measure_dominant_kernel(model, reps=5):
     return out
 
 
+def side_measurements(precision):
+    """BASELINE configs[1] (single encoder / decoder residual cell fwd and fwd+bwd, NHWC batch 256 at 14x14x64 and 7x7x128)
+    and configs[3] (decoder-only sampling, temperature 0.7, batch 1024), reported under `extra` so the driver's record
+    carries them.  Each is a CUDA graph replayed with the L2 flushed before every repetition, CUDA-event timed."""
+    import torch
+    from nvae_tf_b200 import runtime as R
+    from nvae_tf_b200.decoder import GenerativeResidualCell
+    from nvae_tf_b200.encoder import EncodingResidualCell
+    from nvae_tf_b200.models import NVAE
+    from nvae_tf_b200.runtime import DeviceTensor
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return statistics.median(ts)
+
+    cells = []
+    for kind, shp in (("enc", (256, 14, 14, 64)), ("enc", (256, 7, 7, 128)), ("dec", (256, 14, 14, 64)),
+                      ("dec", (256, 7, 7, 128))):
+        rt = R.Runtime(seed=1, precision=precision)
+        with rt:
+            N, H, W, Cc = shp
+            cell = (EncodingResidualCell if kind == "enc" else GenerativeResidualCell)(Cc, name="cell")
+            rt.finalize()
+            rt.spectral_normalize_all(power_iter=True)
+            rt.sn_done = True
+            x = DeviceTensor(torch.randn(*shp, device="cuda"))
+            dy = torch.randn(*shp, device="cuda")
+
+            def fwd():
+                return cell(x, training=True)
+
+            def fwdbwd():
+                x.grad = None
+                with rt.gradient_tape() as tape:
+                    y = cell(x, training=True)
+                y.grad = dy
+                rt.backward(tape)
+            us = []
+            for f in (fwd, fwdbwd):
+                f()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                st = torch.cuda.Stream()
+                st.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.graph(g, stream=st):
+                    f()
+                us.append(timed(g.replay))
+            px = N * H * W
+            macs = px * (2 * 9 * Cc * Cc) if kind == "enc" else px * (2 * 6 * Cc * Cc)
+            gf = 6.0 * macs / 1e9
+            cells.append({"cell": "EncodingResidualCell" if kind == "enc" else "GenerativeResidualCell", "x": list(shp),
+                          "fwd_us": us[0], "fwd_bwd_us": us[1], "gflop_fwd_bwd": gf, "tflops_fwd_bwd": gf / us[1] * 1e3})
+    n = 1024
+    m = NVAE(**mirror_kwargs(n), training=False, precision=precision, seed=1)
+    replay = m.capture_sample(n_samples=n, temperature=0.7)
+    us = timed(replay, reps=5)
+    sampling = {"n_samples": n, "temperature": 0.7, "ms": us / 1e3, "images_per_s": n / (us * 1e-6),
+                "tflops_algorithmic": 12.1e9 * n / (us * 1e-6) / 1e12, "kernels": m.sample_graph_kernels,
+                "api": "NVAE.capture_sample(1024, 0.7) replay (one CUDA graph)"}
+    return {"configs[1]_cells": cells, "configs[3]_sampling": sampling}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -198,8 +327,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--precision", default=os.environ.get("NVAE_PRECISION", "auto"), choices=["auto", "fp32", "tf32", "tf32x3"])
-    ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU sample")
+    ap.add_argument("--cpu-batch", type=int, default=BATCH, help="batch of the CPU arm's steps (144 = the GPU arm's config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="mnist", choices=sorted(CONFIGS), help="mnist = BASELINE configs[2]; cifar = configs[4]")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[1] / configs[3] side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -227,14 +358,16 @@ def main():
     precision = {"fp32": _lib.NVAE_PREC_FP32, "tf32": _lib.NVAE_PREC_TF32, "tf32x3": _lib.NVAE_PREC_TF32X3,
                  "auto": _lib.default_precision()}[args.precision]
     B = args.batch
-    model = NVAE(**mirror_kwargs(B), training=True, precision=precision, seed=1)
+    CFG = CONFIGS[args.config]
+    img_shape = (B, 32, 32, CFG["channels"])
+    model = NVAE(**mirror_kwargs(B, args.config), training=True, precision=precision, seed=1)
     model.compile(optimizer=Adamax(learning_rate=CosineDecay(1e-3, 400 * 417)), run_eagerly=True)
     if world > 1:
         parallel.broadcast_parameters([model.rt.params, model.rt.state])
     model.steps = 20000  # inside the KL warm-up: beta < 1, balancing active (the common case of the first 30 %)
-    train_fn = model.make_train_function((B, 32, 32, 1))
+    train_fn = model.make_train_function(img_shape)
     static_in, replay = train_fn.static_in, train_fn.replay
-    x = torch.as_tensor(synthetic_images(B, 1 + rank)).to(model.rt.device)
+    x = torch.as_tensor(synthetic_images(B, 1 + rank, args.config)).to(model.rt.device)
     static_in.copy_(x)
 
     def barrier():
@@ -265,7 +398,7 @@ def main():
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end to end through the host-batch API -------------------------------------------------------------
-    host_batches = [torch.as_tensor(synthetic_images(B, 100 + rank + i)).pin_memory() for i in range(4)]
+    host_batches = [torch.as_tensor(synthetic_images(B, 100 + rank + i, args.config)).pin_memory() for i in range(4)]
     for i in range(2):
         train_fn(host_batches[i % 4])
     barrier()
@@ -282,6 +415,16 @@ def main():
            "d2h_bytes_per_step": train_fn.d2h_bytes, "ms_per_step": e2e_ms / args.steps,
            "api": "NVAE.make_train_function(batch_shape)(host_batch)"}
 
+    # ---- data-parallel consistency: every rank must hold bit-identical parameters after all those steps ---------------
+    replicas_identical = None
+    if world > 1:
+        pd = model.rt.params.double()
+        mine = torch.stack([pd.sum(), (pd * pd).sum(), pd.abs().max()])
+        lo, hi = mine.clone(), mine.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        replicas_identical = bool(torch.equal(lo, hi))
+        assert replicas_identical, f"rank {rank}: parameter checksums differ across ranks: {lo.tolist()} vs {hi.tolist()}"
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -300,9 +443,8 @@ def main():
     arith = ("3xFP16: amax-scaled fp16 hi/lo split, A via TMEM, pre-split B via TMA, two accumulators per CTA" if f16 else
              "3xTF32 split in-kernel, A via TMEM" if x3 else "single-pass TF32")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01i_ncu_*.md /
-                # r01h for 3xTF32); algorithmic bytes are 127.9 MB (x + w + y once)
-                "traffic": DOMINANT_TRAFFIC_F16 if f16 else (113.3e6 if x3 else None),
+                # algorithmic bytes are 127.9 MB (x + w + y once)
+                "traffic": dominant_traffic(f16, x3)[0], "traffic_source": dominant_traffic(f16, x3)[1],
                 "mma_issue_factor": 3 if x3 else 1,
                 "issued_mma_frac": (3 if x3 else 1) * achieved / peak,
                 "note": ("fp32-grade products cost 3 MMAs each (hi*hi + hi*lo + lo*hi), so the ceiling of frac is 1/3; "
@@ -315,21 +457,26 @@ def main():
                 "flops_per_launch": dom["flops"], "ms_per_launch": dom["ms"],
                 "peak_source": (("MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590 bf16 TFLOP/s") +
                                 ("" if f16 else " / 2 for TF32")),
-                "step_tensor_frac": (FLOP_PER_IMAGE * B / ((ms / args.steps) * 1e-3) / 1e12) /
+                "step_tensor_frac": (CFG["flop_per_image"] * B / ((ms / args.steps) * 1e-3) / 1e12) /
                                     (peaks.get("bf16_tflops_sustained", 1400.0) / (1.0 if f16 else 2.0))}
-    cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(args.cpu_batch)
+    cpu = None if (args.no_cpu_baseline or world > 1 or args.config != "mnist") else cpu_baseline(args.cpu_batch)
+    extra = None
+    if world == 1 and not args.no_extras and args.config == "mnist":
+        del train_fn, static_in, replay
+        extra = side_measurements(precision)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": ("f16x3+tf32x3" if f16 else "tf32x3" if x3 else "tf32") if tc else "f32", "data": "synthetic",
-            "config": {"workload": "full MNIST-config NVAE train step (train.py defaults: 40.1M params, 15 latent "
-                                   "groups, KL+recon+BN-gamma loss, SN, Adamax), BASELINE configs[2]",
-                       "batch_per_gpu": B, "global_batch": B * world, "image": "32x32x1",
+            "config": {"workload": CFG["workload"],
+                       "batch_per_gpu": B, "global_batch": B * world, "image": f"32x32x{CFG['channels']}",
+                       "parameters": int(model.rt.n_trainable()),
                        "parallelism": f"dp{world}", "training_mode": "batch-stat BN + SN power iteration",
                        "l2": "per-step working set ~6 GB of activations >> 126 MB L2 (no explicit flush needed)",
                        "execution": "one CUDA graph per step" + ("" if world == 1 else " + NCCL all-reduce + Adamax")},
             "e2e": e2e, "gpu_launches": model.graph_kernels * args.steps, "kernels_per_step": model.graph_kernels,
             "launcher_calls_per_step": model.graph_launches,
-            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "final_loss": loss, "e2e_loss": res["loss"]}
+            "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "final_loss": loss, "e2e_loss": res["loss"],
+            "replicas_identical": replicas_identical, "extra": extra}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

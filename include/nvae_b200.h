@@ -170,6 +170,13 @@ NVAE_API int nvae_bernoulli_ll_fwd(const float* logits, const float* x, int B, i
 NVAE_API int nvae_bernoulli_ll_bwd(const float* logits, const float* x, int B, int H, int W, int C, int Cl, float scale,
                           float* dlogits, nvae_stream_t stream);
 
+/* Importance-weighted NLL bound over K attempts.   Replaces: evaluate.py:111-123 (tf.stack + reduce_logsumexp +
+ * reduce_mean).  recon/log_q/log_p are [K,B] (row k = attempt k: calculate_recon_loss(crop_output=True), and the
+ * log q / log p sums of model(batch, nll=True));  per_sample[B] (nullable) = logsumexp_k(-recon - log_q + log_p) - log K;
+ * nll[0] = -mean_b per_sample. */
+NVAE_API int nvae_iwae_nll(const float* recon, const float* log_q, const float* log_p, int K, int B, float* per_sample,
+                  float* nll, nvae_stream_t stream);
+
 /* BN-gamma infinity-norm regulariser.   Replaces: models.py:252-267 (88 x (abs,max) launches).
  * gamma k lives at params+offsets[k] with sizes[k] elements (device tables). */
 NVAE_API int nvae_bn_loss_fwd(const float* params, const int64_t* offsets, const int32_t* sizes, int n, float sr_lambda,

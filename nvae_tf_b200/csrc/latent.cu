@@ -300,6 +300,49 @@ extern "C" int nvae_bernoulli_ll_bwd(const float* logits, const float* x, int B,
   return NVAE_OK;
 }
 
+// Importance-weighted bound (evaluate.py:111-123): log_iw[k,b] = -recon[k,b] - log_q[k,b] + log_p[k,b];
+// per_sample[b] = logsumexp_k log_iw[k,b] - log K;  nll = -mean_b per_sample.  One block, fixed-order tree: deterministic.
+namespace nvae {
+__global__ void __launch_bounds__(256) iwae_nll_kernel(const float* __restrict__ recon, const float* __restrict__ log_q,
+                                                       const float* __restrict__ log_p, int K, int B,
+                                                       float* __restrict__ per_sample, float* __restrict__ nll) {
+  nvae::pdl_enter();
+  __shared__ float red[256];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float m = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      const int64_t i = (int64_t)k * B + b;
+      m = fmaxf(m, -recon[i] - log_q[i] + log_p[i]);
+    }
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int64_t i = (int64_t)k * B + b;
+      s += expf(-recon[i] - log_q[i] + log_p[i] - m);
+    }
+    const float v = m + logf(s) - logf((float)K);
+    if (per_sample) per_sample[b] = v;
+    acc += v;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) nll[0] = -red[0] / (float)B;
+}
+}  // namespace nvae
+
+extern "C" int nvae_iwae_nll(const float* recon, const float* log_q, const float* log_p, int K, int B, float* per_sample,
+                             float* nll, nvae_stream_t stream) {
+  if (K <= 0 || B <= 0) return NVAE_E_BADSHAPE;
+  if (!recon || !log_q || !log_p || !nll) return NVAE_E_NULLPTR;
+  nvae::launch(nvae::iwae_nll_kernel, 1, 256, 0, stream, recon, log_q, log_p, K, B, per_sample, nll);
+  NVAE_RETURN_IF_LAUNCH_FAILED();
+  return NVAE_OK;
+}
+
 extern "C" int nvae_bn_loss_fwd(const float* params, const int64_t* offsets, const int32_t* sizes, int n,
                                 float sr_lambda, float* loss, nvae_stream_t stream) {
   if (n <= 0 || n > 1024) return NVAE_E_BADSHAPE;

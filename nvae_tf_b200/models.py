@@ -98,6 +98,10 @@ class NVAE:
         self._beta_one = torch.ones(8, device=rt.device)
         self._m = self._v = None
         self._graph = None
+        # data parallel: identical weights on every rank (same `seed`) but independent epsilon streams -- the Philox key
+        # folds the rank in, so the replicas of a global batch do not draw the same noise
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rt.philox_seed = (seed + 0x9E3779B1 * torch.distributed.get_rank(process_group)) & 0xFFFFFFFFFFFFFFFF
 
     # ---- Keras-model surface ---------------------------------------------------------------------
     @property
@@ -113,11 +117,36 @@ class NVAE:
         self._v = torch.zeros_like(self.rt.params)
 
     def save_weights(self, path: str) -> None:
-        np.savez(path, __steps=self.steps, __epoch=self.epoch, **self.rt.named_values())
+        """Keras `save_weights` (train.py:51): variables under the reference's attribute paths plus what a TF-format
+        checkpoint also carries -- the optimizer slots (Adamax m / v per variable, `optimizer/m/<name>`) and its
+        iteration counter -- and the warm-up position (`steps`, `epoch`; train.py:133-135 re-derives them from the
+        file name, here they travel with the file)."""
+        extra = {"__steps": self.steps, "__epoch": self.epoch, "__optimizer_iterations": int(self._counters[1].item())}
+        if self._m is not None:
+            m, v = self._m.detach().cpu().numpy(), self._v.detach().cpu().numpy()
+            for var in self.rt.trainable_variables:
+                extra["__optimizer/m/" + var.name] = m[var.offset:var.offset + var.size].reshape(var.shape)
+                extra["__optimizer/v/" + var.name] = v[var.offset:var.offset + var.size].reshape(var.shape)
+        np.savez(path, **extra, **self.rt.named_values())
 
     def load_weights(self, path: str) -> None:
+        """Restores variables, and -- when the file has them and compile() ran -- the Adamax slots, the optimizer
+        iteration count (CosineDecay position, bias correction) and steps / epoch, so a resumed run continues the
+        schedules where the saved one stopped."""
         with np.load(path if path.endswith(".npz") else path + ".npz") as f:
             self.rt.load_named({k: f[k] for k in f.files if not k.startswith("__")})
+            if "__steps" in f.files:
+                self.steps, self.epoch = int(f["__steps"]), int(f["__epoch"])
+            if "__optimizer_iterations" in f.files:
+                self._counters[1] = int(f["__optimizer_iterations"])
+            if self._m is not None:
+                for var in self.rt.trainable_variables:
+                    for slot, arena in (("m", self._m), ("v", self._v)):
+                        key = f"__optimizer/{slot}/{var.name}"
+                        if key in f.files:
+                            arena[var.offset:var.offset + var.size].copy_(
+                                torch.as_tensor(np.asarray(f[key], dtype=np.float32).ravel()))
+        self._host_metric = None  # the device warm-up counter is re-synchronised on the next step / replay
 
     def on_epoch_begin(self, epoch, logs=None):
         self.epoch = epoch
@@ -183,6 +212,9 @@ class NVAE:
         data = self._as_device(data)
         B = data.shape[0]
         self._sync_counters()
+        # Philox stream ids restart every step (the device iteration counter separates the steps), so an eager step and a
+        # replay of the captured graph draw the same epsilons
+        rt.eps_i = 0
         rt.lib.fill(rt.grads.data_ptr(), rt.grads.numel(), 0.0, rt.stream)
         self._schedule(advance=True)
         with rt.gradient_tape() as tape:
@@ -247,11 +279,27 @@ class NVAE:
         prio = -1 if os.environ.get("NVAE_STREAM_PRIO", "1") != "0" else 0
         stream = torch.cuda.Stream(device=rt.device, priority=prio)
         stream.wait_stream(torch.cuda.current_stream(rt.device))
+        # the warm-up steps size the allocator / workspaces with REAL launches on an all-zero batch; everything they
+        # touch (weights, Adamax slots, BN moving statistics, SN u, schedule counters) is put back afterwards, so capture
+        # leaves the model exactly as it found it
+        torch.cuda.synchronize(rt.device)
+        snap = [t.clone() for t in (rt.params, rt.state, self._counters, rt.sn_sigma)] if warmup > 0 else None
+        snap_mv = [self._m.clone(), self._v.clone()] if (warmup > 0 and self._m is not None) else None
+        steps0 = self.steps
         with torch.cuda.stream(stream):
             for _ in range(warmup):
                 out = self.train_step(static_in)
         torch.cuda.current_stream(rt.device).wait_stream(stream)
         torch.cuda.synchronize(rt.device)
+        if snap is not None:
+            for dst, src in zip((rt.params, rt.state, self._counters, rt.sn_sigma), snap):
+                dst.copy_(src)
+            if snap_mv is not None:
+                self._m.copy_(snap_mv[0])
+                self._v.copy_(snap_mv[1])
+            self.steps = steps0
+            self._host_metric = None
+            torch.cuda.synchronize(rt.device)
         self._sync_counters()
         # Kernel nodes record the priority of the stream they were captured on, but a plainly instantiated graph runs
         # every node at the LAUNCH stream's priority: the library instantiates the captured cudaGraph_t with
@@ -279,6 +327,9 @@ class NVAE:
         self._graph = graph
 
         def replay():
+            # host-side changes of the warm-up metric (on_epoch_begin with epoch-based warm-up, `model.steps = n` after
+            # a resume) reach the device counter here: a small H2D write outside the graph, only when it changed
+            self._sync_counters()
             if graph_exec is not None:
                 rc = rt.lib._nvae_graph_launch(graph_exec, rt.stream)
                 if rc != 0:
@@ -296,33 +347,53 @@ class NVAE:
     def make_train_function(self, batch_shape):
         """Keras `make_train_function` analogue for HOST batches: returns f(host_batch) -> dict of host arrays.
         Each call copies the batch host->device (pinned staging), replays the captured step and reads the
-        four losses back device->host -- the end-to-end path bench.py's `e2e` measures."""
-        rt = self.rt
-        static_in, replay = self.capture_train_step(batch_shape)
-        staging = torch.empty(tuple(batch_shape), dtype=torch.float32).pin_memory()
-        B = batch_shape[0]
-        host_out = torch.empty(2 * B + 2, dtype=torch.float32).pin_memory()
-        dev_out = torch.empty(2 * B + 2, device=rt.device)
+        four losses back device->host -- the end-to-end path bench.py's `e2e` measures.
+
+        A batch of a different size than `batch_shape` (the reference's last batch of an epoch is 96 of 144,
+        SURVEY 3.1) gets its own captured graph the first time it is seen (cached per shape); capture leaves the
+        model state untouched, so switching shapes mid-epoch is exact."""
+        fns = {}
+
+        def build(shape):
+            rt = self.rt
+            static_in, replay = self.capture_train_step(shape)
+            staging = torch.empty(tuple(shape), dtype=torch.float32).pin_memory()
+            B = shape[0]
+            host_out = torch.empty(2 * B + 2, dtype=torch.float32).pin_memory()
+            dev_out = torch.empty(2 * B + 2, device=rt.device)
+
+            def run(batch):
+                if isinstance(batch, torch.Tensor) and batch.is_pinned():
+                    static_in.copy_(batch, non_blocking=True)
+                else:
+                    staging.copy_(torch.as_tensor(batch, dtype=torch.float32))
+                    static_in.copy_(staging, non_blocking=True)
+                out = replay()
+                dev_out[0:1].copy_(out["loss"].reshape(1))
+                dev_out[1:2].copy_(out["bn_loss"].reshape(1))
+                dev_out[2:2 + B].copy_(out["reconstruction_loss"])
+                dev_out[2 + B:].copy_(out["kl_loss"])
+                host_out.copy_(dev_out, non_blocking=True)
+                torch.cuda.current_stream(rt.device).synchronize()
+                h = host_out.numpy()
+                return {"loss": float(h[0]), "bn_loss": float(h[1]), "reconstruction_loss": h[2:2 + B],
+                        "kl_loss": h[2 + B:]}
+            run.static_in, run.replay = static_in, replay
+            return run
+
+        main_shape = tuple(int(v) for v in batch_shape)
+        fns[main_shape] = build(main_shape)
 
         def train_function(batch):
-            if isinstance(batch, torch.Tensor) and batch.is_pinned():
-                static_in.copy_(batch, non_blocking=True)
-            else:
-                staging.copy_(torch.as_tensor(batch, dtype=torch.float32))
-                static_in.copy_(staging, non_blocking=True)
-            out = replay()
-            dev_out[0:1].copy_(out["loss"].reshape(1))
-            dev_out[1:2].copy_(out["bn_loss"].reshape(1))
-            dev_out[2:2 + B].copy_(out["reconstruction_loss"])
-            dev_out[2 + B:].copy_(out["kl_loss"])
-            host_out.copy_(dev_out, non_blocking=True)
-            torch.cuda.current_stream(rt.device).synchronize()
-            h = host_out.numpy()
-            return {"loss": float(h[0]), "bn_loss": float(h[1]), "reconstruction_loss": h[2:2 + B],
-                    "kl_loss": h[2 + B:]}
-        train_function.static_in, train_function.replay = static_in, replay
-        train_function.h2d_bytes = int(np.prod(batch_shape)) * 4
-        train_function.d2h_bytes = (2 * B + 2) * 4
+            shape = tuple(int(v) for v in batch.shape)
+            fn = fns.get(shape)
+            if fn is None:
+                fn = fns[shape] = build(shape)
+            return fn(batch)
+        train_function.static_in, train_function.replay = fns[main_shape].static_in, fns[main_shape].replay
+        train_function.h2d_bytes = int(np.prod(main_shape)) * 4
+        train_function.d2h_bytes = (2 * main_shape[0] + 2) * 4
+        train_function.captured_shapes = fns
         return train_function
 
     # ---- sampling (models.py:137-189) ---------------------------------------------------------------------
@@ -369,6 +440,48 @@ class NVAE:
         z2 = dec.sampler.sample(mu, sigma)
         # images and the last hierarchical z's (mu, sigma, s) so sample_with_z can re-render (models.py:177-178)
         return images, last_s, z1, z2
+
+    def capture_sample(self, n_samples=16, temperature=1.0, greyscale=True, warmup: int = 1):
+        """`sample()` as ONE CUDA graph (BASELINE configs[3]: ~330 launches for 1024 images).  Returns replay() ->
+        (images, last_s, z1, z2), the same static device buffers every call.  The epsilons come from Philox keyed by a
+        device counter that a node of the graph advances, so every replay draws fresh noise; the operand copies of the
+        kernels are refreshed inside the graph, so weights moved by training are picked up."""
+        rt = self.rt
+        if rt.eps_injected is not None:
+            raise RuntimeError("graph capture draws epsilon on device (Philox); clear the injected epsilons")
+        if not hasattr(self, "_sample_counters"):
+            self._sample_counters = torch.zeros(2, dtype=torch.int64, device=rt.device)
+            self._sample_hyper = torch.zeros(8, device=rt.device)
+        stream = torch.cuda.Stream(device=rt.device)
+        stream.wait_stream(torch.cuda.current_stream(rt.device))
+
+        def body():
+            rt.eps_i = 0
+            prev, rt.counters = rt.counters, self._sample_counters
+            try:
+                out = self.sample(n_samples, temperature, greyscale)
+                # ++counters[1]: the next replay's Philox step
+                rt.lib.schedule_step(self._sample_counters.data_ptr(), self._sample_hyper.data_ptr(), 0.0, 0.0, 0.0, 0.9,
+                                     2, rt.stream)
+            finally:
+                rt.counters = prev
+            return out
+        with torch.cuda.stream(stream):
+            for _ in range(max(warmup, 1)):
+                body()
+        torch.cuda.current_stream(rt.device).wait_stream(stream)
+        torch.cuda.synchronize(rt.device)
+        graph = torch.cuda.CUDAGraph()
+        k0 = rt.lib._nvae_launch_count()
+        with torch.cuda.graph(graph, stream=stream):
+            out = body()
+        self.sample_graph_kernels = rt.lib._nvae_launch_count() - k0
+        self._sample_graph = graph
+
+        def replay():
+            graph.replay()
+            return out
+        return replay
 
     def _bernoulli_images(self, logits: DeviceTensor, greyscale: bool = True) -> torch.Tensor:
         """distributions.Bernoulli(logits).probs_parameter()/mean() = sigmoid(l); sample() = U < sigmoid(l)."""

@@ -112,6 +112,7 @@ class Runtime:
         self.tape: Optional[List[Callable[[], None]]] = None
         self.params = self.grads = self.state = None
         self._ws: Dict[str, torch.Tensor] = {}
+        self._ws_retired: List[torch.Tensor] = []
         self._side: Optional[torch.cuda.Stream] = None
         self._on_side = False
         self._side_dirty = False
@@ -232,6 +233,8 @@ class Runtime:
             if torch.cuda.is_current_stream_capturing():
                 raise _lib.NvaeError("workspace must be sized by an eager warm-up step before graph capture")
             torch.cuda.synchronize(self.device)  # nothing in flight may still be using the old buffer
+            if ws is not None:
+                self._ws_retired.append(ws)  # an already-captured graph (another batch shape) may have its address baked in
             ws = self._ws[key] = torch.empty(max(nbytes, 32 << 20), dtype=torch.uint8, device=self.device)
         return ws.data_ptr(), ws.numel()
 
@@ -588,7 +591,10 @@ def conv2d(rt: Runtime, x: DeviceTensor, conv, x2: Optional[DeviceTensor] = None
             if residual is not None:
                 if d.y_ld not in (0, d.Cout):
                     raise NotImplementedError("residual with a concatenated output")
-                rt.add_grad(residual, dy, take=out is None)
+                # the side-stream wgrad above still reads dy: adopting the buffer as residual.grad would let later
+                # main-stream accumulations (se_bwd / bn_act_bwd with accum=1) overwrite it under the reader, so with
+                # the side stream on the residual gets its own copy (one axpby of a 2-5 MB tensor)
+                rt.add_grad(residual, dy, take=out is None and not rt.use_side_stream)
             if out is None:
                 y.grad = None
         rt.record(bwd)

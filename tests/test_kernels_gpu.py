@@ -323,6 +323,32 @@ def test_conv2d_full_size_3xfp16_agrees_with_3xtf32(lib_built, shape, monkeypatc
             ey = float((res[mode][0][:1] - yo.detach()).abs().max() / yo.detach().abs().max())
             ex = float((res[mode][1][:1] - xo.grad).abs().max() / xo.grad.abs().max())
             assert ey <= tol and ex <= tol, f"NVAE_F16X3={mode}: y {ey:.2e}, dx {ex:.2e} vs float64"
+        # the full-size FILTER gradient of both arithmetics against float64 (batch 144: the pixel-aligned split-K, nsub /
+        # dual tiles).  dw[r,s,ci,co] = sum_pixels x[n,h+r-2,w+s-2,ci] * dy[n,h,w,co]: a float64 GEMM on the device over
+        # ALL pixels for a sample of taps (corners, centre, an edge) and 16 input channels each -- 6 144 (or 3 072) of the
+        # filter's entries per tap, every one a sum over all 36 864 / 147 456 pixels
+        xd, dyd = x.to(rt.device).double(), dy.to(rt.device).double()
+        xp = torch.nn.functional.pad(xd, (0, 0, 2, 2, 2, 2))  # SAME padding of a 5x5 stride-1 conv: 2 before, 2 after
+        ci = torch.arange(0, Cin, Cin // 16, device=rt.device)[:16]
+        dyf = dyd.reshape(-1, Cout)
+        for (r, sx) in ((0, 0), (2, 2), (4, 4), (1, 3), (4, 0)):
+            xs = xp[:, r:r + Hh, sx:sx + W, :][..., ci].reshape(-1, ci.numel())
+            ref = (xs.t() @ dyf).cpu()                                    # [16, Cout] float64
+            for mode, tol in (("1", 1e-4), ("0", 2e-4)):
+                got = res[mode][2][r, sx][ci.cpu()]
+                err = float((got - ref).abs().max() / ref.abs().max())
+                assert err <= tol, f"NVAE_F16X3={mode}: dw tap ({r},{sx}) vs float64: {err:.2e}"
+        # forward over ALL images against a float64 device GEMM for a sample of output channels (im2col of 16 columns)
+        wv = torch.as_tensor(npy(conv.kernel.value)).to(rt.device)       # [5,5,Cin,Cout] float64
+        co = torch.arange(0, Cout, Cout // 8, device=rt.device)[:8]
+        yref = torch.zeros(N, Hh, W, co.numel(), dtype=torch.float64, device=rt.device)
+        for r in range(5):
+            for sx in range(5):
+                yref += xp[:, r:r + Hh, sx:sx + W, :] @ wv[r, sx][:, co]
+        for mode, tol in (("1", 1e-4), ("0", 2e-4)):
+            got = res[mode][0][..., co.cpu()]
+            err = float((got - yref.cpu()).abs().max() / yref.abs().max())
+            assert err <= tol, f"NVAE_F16X3={mode}: y (all images) vs float64: {err:.2e}"
 
 
 def test_conv2d_concat_output_and_accumulating_dgrad(rt):

@@ -275,23 +275,147 @@ def test_sampling_matches_oracle(lib_built):
 
 
 def test_cuda_graph_replay_equals_eager(lib_built):
-    """The captured whole-step graph reproduces the eager step (same Philox epsilons from device counters)."""
+    """The captured whole-step graph IS the eager step: after 5 steps every parameter, every Adamax slot and every
+    moving statistic is bit-identical (Philox epsilons are keyed by the device iteration counter + the group index, and
+    capture leaves the model untouched)."""
     cfg = H.oracle_cfg()
     x = torch.as_tensor(O.make_images(cfg, 4, seed=3).numpy().astype(np.float32))
     res = []
     for mode in ("eager", "graph"):
         m = _make_model(cfg, 4, True, seed=5)
+        m.steps = 7
         if mode == "eager":
             outs = [m.train_step(x.cuda()) for _ in range(5)]
             loss = outs[-1]["loss"].item()
         else:
-            static_in, replay = m.capture_train_step((4, 32, 32, 1), warmup=2)  # 2 eager + 1 captured-not-run
+            before = (m.rt.params.clone(), m.rt.state.clone(), m._counters.clone())
+            static_in, replay = m.capture_train_step((4, 32, 32, 1), warmup=2)
+            torch.cuda.synchronize()
+            assert torch.equal(before[0], m.rt.params) and torch.equal(before[1], m.rt.state)  # capture mutates nothing
+            assert torch.equal(before[2], m._counters) and m.steps == 7
+            assert float(m._m.abs().max()) == 0.0 and float(m._v.abs().max()) == 0.0
             static_in.copy_(x)
-            for _ in range(3):
+            for _ in range(5):
                 out = replay()
             loss = out["loss"].item()
             assert m.graph_launches > 100
         torch.cuda.synchronize()
-        res.append((loss, m.rt.params.clone()))
-    assert np.isfinite(res[0][0]) and np.isfinite(res[1][0])
-    assert res[0][1].shape == res[1][1].shape
+        assert m.steps == 12
+        res.append((loss, m.rt.params.clone(), m.rt.state.clone(), m._m.clone(), m._v.clone()))
+    assert res[0][0] == res[1][0]
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert torch.equal(a, b)
+
+
+def test_graph_replay_follows_epoch_based_warmup(lib_built):
+    """train.py default: --step_based_warmup off, beta = min(epoch / (0.3 n_total), 1) moves only in on_epoch_begin
+    (models.py:121-122).  The replayed graph must see the new epoch (it used to keep the capture-time beta)."""
+    cfg = H.oracle_cfg(step_based_warmup=False, n_total_iterations=20)
+    x = torch.as_tensor(O.make_images(cfg, 4, seed=4).numpy().astype(np.float32)).cuda()
+    runs = []
+    for mode in ("eager", "graph"):
+        m = _make_model(cfg, 4, True, seed=6)
+        step = (lambda: m.train_step(x)) if mode == "eager" else None
+        if mode == "graph":
+            static_in, replay = m.capture_train_step((4, 32, 32, 1))
+            static_in.copy_(x)
+            step = replay
+        seen = []
+        for epoch in (0, 0, 3, 3, 9):
+            m.on_epoch_begin(epoch)
+            out = step()
+            torch.cuda.synchronize()
+            seen.append((float(m._hyper[0].item()), out["kl_loss"].clone(), float(out["loss"].item())))
+        runs.append(seen)
+    betas = [b for b, _, _ in runs[1]]
+    assert betas == [0.0, 0.0, 0.5, 0.5, 1.0], betas
+    for (b0, k0, l0), (b1, k1, l1) in zip(*runs):
+        assert b0 == b1 and torch.equal(k0, k1) and l0 == l1
+    assert float(runs[1][2][1].abs().max()) > 0.0  # KL really is weighted in once beta > 0
+
+
+def test_checkpoint_round_trip_resumes_the_schedules(lib_built, tmp_path):
+    """save_weights / load_weights carry the variables AND the optimizer slots, iteration count and warm-up position
+    (Keras TF-format checkpoints do; train.py:133-135): a resumed model takes bit-identical next steps."""
+    cfg = H.oracle_cfg()
+    x = torch.as_tensor(O.make_images(cfg, 4, seed=5).numpy().astype(np.float32)).cuda()
+    a = _make_model(cfg, 4, True, seed=8)
+    for _ in range(3):
+        a.train_step(x)
+    path = str(tmp_path / "epoch_3")
+    a.save_weights(path)
+    b = _make_model(cfg, 4, True, seed=99)  # different init: everything must come from the file
+    b.load_weights(path)
+    assert b.steps == a.steps == 3 and int(b._counters[1].item()) == 3
+    assert torch.equal(a.rt.params, b.rt.params) and torch.equal(a.rt.state, b.rt.state)
+    assert torch.equal(a._m, b._m) and torch.equal(a._v, b._v)
+    b.rt.philox_seed = a.rt.philox_seed
+    oa, ob = a.train_step(x), b.train_step(x)
+    torch.cuda.synchronize()
+    assert oa["loss"].item() == ob["loss"].item() and torch.equal(a.rt.params, b.rt.params)
+    assert float(b._hyper[3].item()) == 4.0  # Adamax bias-correction step t continued at 4, not restarted at 1
+
+
+def test_train_function_handles_the_short_last_batch(lib_built):
+    """The reference's last batch of an epoch is smaller (96 of 144): make_train_function captures a second
+    graph for the new shape and the result equals the eager step on the same state."""
+    cfg = H.oracle_cfg()
+    x6 = O.make_images(cfg, 6, seed=6).numpy().astype(np.float32)
+    x4 = O.make_images(cfg, 4, seed=7).numpy().astype(np.float32)
+    m = _make_model(cfg, 6, True, seed=9)
+    e = _make_model(cfg, 6, True, seed=9)
+    fn = m.make_train_function((6, 32, 32, 1))
+    r1, r2, r3 = fn(x6), fn(x4), fn(x6)
+    o = [e.train_step(torch.as_tensor(v).cuda()) for v in (x6, x4, x6)]
+    torch.cuda.synchronize()
+    assert len(fn.captured_shapes) == 2 and r2["kl_loss"].shape == (4,)
+    assert r1["loss"] == o[0]["loss"].item() and r2["loss"] == o[1]["loss"].item() and r3["loss"] == o[2]["loss"].item()
+    assert torch.equal(m.rt.params, e.rt.params)
+
+
+def test_neg_log_likelihood_matches_oracle(lib_built):
+    """evaluate.py:111-123: k-attempt importance-weighted bound with the 28x28 crop, logsumexp on the device."""
+    from nvae_tf_b200.evaluate import batch_neg_log_likelihood, neg_log_likelihood
+    cfg = H.oracle_cfg()
+    params, trainable, bnl, s = O.build_params(cfg, seed=12, jitter=0.1)
+    params = {k: f32(v) for k, v in params.items()}
+    x = O.make_images(cfg, 5, seed=12).numpy()
+    K = 3
+    eps = [[f32(e.numpy()) for e in O.make_eps(s, 5, seed=20 + k)] for k in range(K)]
+    m = _make_model(cfg, 5, False)
+    m.rt.load_named(params)
+    m.rt.inject_eps([e for att in eps for e in att])  # attempt k consumes the k-th run of per-group epsilons
+    got = float(batch_neg_log_likelihood(m, x, n_attempts=K).item())
+    logs = []
+    for k in range(K):
+        c = O.Ctx(O.to_torch(params, []), False, [H.t64(e) for e in eps[k]])
+        lo, _, lp, lq = O.nvae_call(c, s, H.t64(x), nll=True)
+        logs.append(-O.calculate_recon_loss(H.t64(x), lo, True) - lq + lp)
+    want = float(-(torch.logsumexp(torch.stack(logs), 0) - np.log(K)).mean())
+    assert abs(got - want) <= TOL_LOSS * abs(want), (got, want)
+    m.rt.inject_eps(None)
+    metric = neg_log_likelihood(m, [(x, None), (x[:3], None)], n_attempts=2)
+    assert np.isfinite(metric.mean) and metric.stddev >= 0.0
+
+
+def test_sample_graph_replay(lib_built):
+    """NVAE.capture_sample: the whole ancestral-sampling pass as one CUDA graph; each replay draws fresh epsilons and
+    picks up retrained weights."""
+    cfg = H.oracle_cfg()
+    m = _make_model(cfg, 4, False, seed=4)
+    replay = m.capture_sample(n_samples=8, temperature=0.7)
+    a = replay()[0].clone()
+    b = replay()[0].clone()
+    torch.cuda.synchronize()
+    assert a.shape == (8, 32, 32, 1) and float(a.min()) >= 0.0 and float(a.max()) <= 1.0
+    assert not torch.equal(a, b)  # new noise per replay
+    assert m.sample_graph_kernels > 20
+    # same counter value + same weights -> same images as the eager call
+    m._sample_counters.zero_()
+    g0 = replay()[0].clone()
+    prev, m.rt.counters = m.rt.counters, torch.zeros(2, dtype=torch.int64, device=m.rt.device)
+    m.rt.eps_i = 0
+    e0 = m.sample(n_samples=8, temperature=0.7)[0]
+    m.rt.counters = prev
+    torch.cuda.synchronize()
+    assert torch.equal(g0, e0)

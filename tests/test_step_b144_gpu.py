@@ -1,0 +1,136 @@
+"""Parity of the BENCHMARKED configuration: default-config NVAE train step at batch 144 (BASELINE configs[2]).
+
+Batch 144 takes code paths the small-batch tests never reach -- 3xFP16 eligibility (>= 20 GFLOP), nsub / dual tiles,
+the pixel-aligned split-K of the 226 MB filter gradient, the cluster-BN size limits and the split BN kernels for the
+57-113 MB tensors, the CUDA-graph replay bench.py times.  Checked here:
+  (i)   default arithmetic, CUDA-graph replay  vs  NVAE_PRECISION=fp32 (CUDA-core FFMA, an independent arithmetic path
+        on the same device): every gradient tensor and every moving statistic / SN vector <= 1e-3;
+  (ii)  default arithmetic, eager, injected epsilons  vs  the float64 oracle: the four losses and kl_all [15,144];
+  (iii) weight-gradient side stream on vs off: bit-identical gradients (the side stream only reorders launches).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import nvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+B = 144
+TOL = 1e-3
+
+
+def _model(precision=None, seed=1):
+    from nvae_tf_b200.models import NVAE, Adamax, CosineDecay
+    cfg = O.NVAEConfig()
+    m = NVAE(**H.mirror_kwargs(cfg, B), training=True, precision=precision, seed=seed)
+    m.compile(optimizer=Adamax(learning_rate=CosineDecay(1e-3, 400 * 417)), run_eagerly=True)
+    m.steps = 20000  # inside the KL warm-up: beta < 1, balancing on (what bench.py runs)
+    return m
+
+
+def _images(seed=1):
+    rng = np.random.default_rng(seed)
+    x = (rng.random((B, 28, 28, 1)) < 0.13).astype(np.float32)
+    return torch.as_tensor(np.pad(x, ((0, 0), (2, 2), (2, 2), (0, 0))))
+
+
+def _rel(a: torch.Tensor, b: torch.Tensor, floor: float) -> float:
+    return float((a.double() - b.double()).abs().max() / max(float(b.double().abs().max()), floor))
+
+
+def test_batch144_graph_replay_matches_fp32_cuda_core_path(lib_built, monkeypatch):
+    from nvae_tf_b200 import _lib
+    monkeypatch.delenv("NVAE_F16X3_MIN_GFLOP", raising=False)
+    monkeypatch.delenv("NVAE_F16X3", raising=False)
+    x = _images()
+    # --- the benchmarked path: default arithmetic (3xFP16 for the six large GEMMs, 3xTF32 elsewhere), graph replay
+    m = _model()
+    # the plan really is the one bench.py times
+    import ctypes as C
+    from nvae_tf_b200 import runtime as R
+    conv = m.postprocess.cells[1].node.cbs2.conv.layer
+    d = R.conv_desc(m.rt, (B, 16, 16, 384), 0, conv.kernel.shape, 1)
+    info = (C.c_int32 * 16)()
+    for which in range(3):
+        m.rt.lib._nvae_conv2d_plan_info(C.byref(d), which, info)
+        assert info[9] == 1, "the dominant GEMM must run 3xFP16 at batch 144"
+    static_in, replay = m.capture_train_step((B, 32, 32, 1))
+    static_in.copy_(x)
+    out = replay()
+    torch.cuda.synchronize()
+    g_tc = m.rt.grads.clone()
+    state_tc = m.rt.state.clone()
+    losses_tc = {k: v.clone() for k, v in out.items()}
+    kl_all_tc = m.decoder.sampler.kl_all.clone()
+    names = [(v.name, v.offset, v.size) for v in m.rt.trainable_variables]
+    snames = [(v.name, v.offset, v.size) for v in m.rt.variables.values() if not v.trainable]
+    del m, static_in, replay, out
+    torch.cuda.empty_cache()
+    # --- the independent arithmetic: fp32 FFMA on CUDA cores, eager, same seed -> same weights, same Philox epsilons
+    f = _model(precision=_lib.NVAE_PREC_FP32)
+    out = f.train_step(x.to(f.rt.device), apply_gradients=False)
+    torch.cuda.synchronize()
+    g_32, state_32 = f.rt.grads, f.rt.state
+    assert abs(float(losses_tc["loss"]) - float(out["loss"])) <= TOL * abs(float(out["loss"]))
+    assert _rel(losses_tc["reconstruction_loss"], out["reconstruction_loss"], 0.0) <= TOL
+    assert _rel(losses_tc["kl_loss"], out["kl_loss"], 1e-3) <= TOL
+    assert _rel(kl_all_tc, f.decoder.sampler.kl_all, 0.0) <= TOL
+    gmax = float(g_32.abs().max())
+    errs = []
+    for n, off, size in names:
+        a, b = g_tc[off:off + size], g_32[off:off + size]
+        bm = float(b.abs().max())
+        if bm <= 1e-9 * gmax + 0.0 or bm < 1e-5 * gmax and n.endswith("bias"):
+            # analytically-zero gradient (bias in front of a training-mode BN): only round-off noise on either side
+            assert float(a.abs().max()) <= 1e-4 * gmax, n
+            continue
+        errs.append((_rel(a, b, 1e-4 * gmax), n))
+    errs.sort(reverse=True)
+    print("batch-144 gradients, tensor-core graph replay vs fp32 CUDA cores: worst", errs[:5],
+          "median %.2e over %d tensors" % (errs[len(errs) // 2][0], len(errs)))
+    assert errs[0][0] <= TOL, errs[:5]
+    for n, off, size in snames:  # BN moving statistics, SN u
+        assert _rel(state_tc[off:off + size], state_32[off:off + size], 1e-6) <= TOL, n
+
+
+def test_batch144_losses_match_float64_oracle(lib_built, monkeypatch):
+    monkeypatch.delenv("NVAE_F16X3_MIN_GFLOP", raising=False)
+    cfg = O.NVAEConfig()
+    params, trainable, bnl, s = O.build_params(cfg, seed=1, jitter=0.05)
+    params = {k: np.asarray(v, np.float32).astype(np.float64) for k, v in params.items()}
+    x = _images(2).numpy()
+    eps = [np.asarray(e.numpy(), np.float32).astype(np.float64) for e in O.make_eps(s, B, seed=2)]
+    m = _model()
+    m.rt.load_named(params)
+    m.rt.inject_eps(eps)
+    out = m.train_step(x, apply_gradients=False)
+    torch.cuda.synchronize()
+    with torch.no_grad():  # forward only: the float64 autograd graph of a batch-144 step would need ~40 GB of host memory
+        ref, _ = O.train_step_loss(cfg, s, O.to_torch(params, []), bnl, H.t64(x), [H.t64(e) for e in eps], 20000,
+                                   training=True)
+    npy = lambda t: t.detach().cpu().numpy().astype(np.float64)
+    assert abs(float(out["loss"].item()) - float(ref["loss"])) <= TOL * abs(float(ref["loss"]))
+    assert abs(float(out["bn_loss"].item()) - float(ref["bn_loss"])) <= TOL * abs(float(ref["bn_loss"]))
+    assert H.max_rel_err(npy(out["reconstruction_loss"]), ref["reconstruction_loss"].numpy()) <= TOL
+    assert H.max_rel_err(npy(out["kl_loss"]), ref["kl_loss"].numpy(), floor=1e-3) <= TOL
+    assert H.max_rel_err(npy(m.decoder.sampler.kl_all), ref["kl_all"].numpy()) <= TOL
+
+
+def test_batch144_weight_gradient_side_stream_is_bit_identical(lib_built, monkeypatch):
+    """the side stream's backward-filter launches read dy while the main stream goes on; any missing
+    happens-before edge shows up as a gradient that differs from the single-stream run."""
+    x = _images(3)
+    grads = []
+    for mode in ("0", "1", "1"):
+        monkeypatch.setenv("NVAE_WGRAD_STREAM", mode)
+        m = _model()
+        assert m.rt.use_side_stream == (mode == "1")
+        m.train_step(x.to(m.rt.device), apply_gradients=False)
+        torch.cuda.synchronize()
+        grads.append(m.rt.grads.clone())
+        del m
+        torch.cuda.empty_cache()
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[1], grads[2])
