@@ -310,6 +310,8 @@ struct TcParams {
                                 // [hi 32 x fp16 | lo 32 x fp16] per 32-deep K chunk that TMA drops into the raw ring) and multiplied
                                 // as hi*hi + hi*lo + lo*hi with kind::f16 -- the same 22 significant bits per operand
                                 // as 3xTF32 at twice the tensor-pipe rate; the epilogue undoes the scales
+  int f16_terms;                // 3 (default): hi*hi + hi*lo + lo*hi.  2 (experiment, NVAE_F16X2=1): the A_hi*B_lo term is not
+                                // issued, i.e. B enters rounded to fp16 (11 significant bits) -- 2/3 of the MMAs
   const float* amax;            // device: {absmax(A operand), absmax(B operand)}, written just before the launch
   int dual;                     // 3xFP16: a CTA tile is TWO 128-row M tiles (mt = 2*(t / n_ntiles) + g) that share every
                                 // staged B tile: stage = [A0][A1][B], converter group g splits A_g, accumulator g at column
@@ -694,6 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         uint64_t db = b_desc0, lb = lb_desc0;
         (void)it;
         const bool f16 = !PAIR && p.f16;
+        const bool three = p.f16_terms != 2;
         const int bns = p.nsub == 2 ? p.BN >> 1 : p.BN;  // columns per MMA / accumulator
         const uint32_t idesc_h = umma_idesc_f16(bns, WGRAD ? 1 : 0);
         const uint64_t sub_step = (uint64_t)(p.b_bytes >> 5);  // second sub-tile's B: half the stage's B bytes, in 16-byte units
@@ -725,8 +728,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + hk * j, idesc_h, accum | (j > 0));
               TC_CYC(it, 9);
+              if (three) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + hlo + hk * j, idesc_h, 1u);
+                for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + hlo + hk * j, idesc_h, 1u);
+              }
               TC_CYC(it, 10);
 #pragma unroll
               for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_lo + 8u * j, db + hk * j, idesc_h, 1u);
@@ -734,8 +739,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const uint32_t acc2 = acc + (uint32_t)p.BN, b_hi = a_hi + 32u, b_lo = a_hi + 48u;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, b_hi + 8u * j, db + hk * j, idesc_h, accum | (j > 0));
+                if (three) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, b_hi + 8u * j, db + hlo + hk * j, idesc_h, 1u);
+                  for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, b_hi + 8u * j, db + hlo + hk * j, idesc_h, 1u);
+                }
 #pragma unroll
                 for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, b_lo + 8u * j, db + hk * j, idesc_h, 1u);
               }
@@ -744,8 +751,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const uint64_t db2 = db + sub_step;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, a_hi + 8u * j, db2 + hk * j, idesc_h, accum | (j > 0));
+                if (three) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, a_hi + 8u * j, db2 + hlo + hk * j, idesc_h, 1u);
+                  for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, a_hi + 8u * j, db2 + hlo + hk * j, idesc_h, 1u);
+                }
 #pragma unroll
                 for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, a_lo + 8u * j, db2 + hk * j, idesc_h, 1u);
               }
@@ -1526,6 +1535,13 @@ bool finish_plan(Plan* pl, int passes, bool wgrad, bool aligned_k = false) {
     pl->stages = (int)(budget / raw);
   }
   if (pl->stages > kMaxStages) pl->stages = kMaxStages;
+  // The converters may run at most `stages` k-units ahead of the oldest TMA load still in flight: a converter warp is
+  // released for unit `it` by lo_empty (MMAs of unit it - lo_stages complete, hence loads <= it - lo_stages landed) and then
+  // waits full[it % stages] by PARITY -- which only tells unit `it` from unit it - stages, not from it - 2*stages.  With
+  // lo_stages > stages it could pass on the parity of the load before last and split a tile that had not landed yet
+  // (found by the bitwise-repeatability test at batch 144: the N = 384 backward-filter ran stages = 3, lo_stages = 4 and
+  // ~1 launch in 13 got one 128-row tile wrong by one k-unit).  So the TMEM A ring is never deeper than the raw ring.
+  if (passes == 3 && pl->lo_stages > pl->stages) pl->lo_stages = pl->stages;
   pl->smem = sizeof(SmemCtl) + 1024 + (size_t)pl->stages * raw + (size_t)pl->lo_stages * lo_slot + sizeof(EpiSmem);
   pl->part_bytes = pl->split ? al256((size_t)pl->G * 2 * ((pl->pair || pl->dual) ? 2 : 1) * kBM * pl->BN * sizeof(float)) : 0;
   return true;
@@ -1561,6 +1577,12 @@ bool use_f16x3(const NvaeConvDesc* d, int which) {
   const double min_gflop = m != nullptr ? atof(m) : 20.0;
   const double gflop = 2.0 * d->N * d->Ho * d->Wo * (double)d->Cout * d->Cin * d->R * d->S * 1e-9;
   return gflop >= min_gflop;
+}
+
+// Experiment: two-term product for the 3xFP16 GEMMs, NVAE_F16X2=1.  Off by default.
+bool f16_two_terms() {
+  const char* e = getenv("NVAE_F16X2");
+  return e != nullptr && e[0] == '1';
 }
 
 // which: 0 forward, 1 dgrad; ntaps: K-loop taps (a stride-2 dgrad launch covers one output parity class)
@@ -1652,6 +1674,7 @@ void fill_common(TcParams* p, const NvaeConvDesc* d, const Plan& pl, float* part
   p->a5d = 0; p->par_c = d->Cin;
   p->tw = pl.t.tw; p->th = pl.t.th; p->tn = pl.t.tn; p->tiles_h = pl.t.tiles_h;
   p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->acc_bufs = pl.acc_bufs; p->pair = pl.pair || pl.dual; p->dual = pl.dual; p->n_mtiles = pl.n_mtiles; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1; p->f16 = pl.f16; p->amax = nullptr; p->nsub = pl.nsub;
+  p->f16_terms = f16_two_terms() ? 2 : 3;
   p->n_ntiles = pl.n_ntiles; p->KU = pl.KU; p->U = pl.U;
   p->T = ((pl.pair || pl.dual) ? (pl.n_mtiles + 1) / 2 : pl.n_mtiles) * pl.n_ntiles; p->whole_tiles = pl.whole_tiles;
   p->a_bytes = pl.a_bytes; p->b_bytes = pl.b_bytes;

@@ -334,7 +334,9 @@ def test_conv2d_full_size_3xfp16_agrees_with_3xtf32(lib_built, shape, monkeypatc
         for (r, sx) in ((0, 0), (2, 2), (4, 4), (1, 3), (4, 0)):
             xs = xp[:, r:r + Hh, sx:sx + W, :][..., ci].reshape(-1, ci.numel())
             ref = (xs.t() @ dyf).cpu()                                    # [16, Cout] float64
-            for mode, tol in (("1", 1e-4), ("0", 2e-4)):
+            # (3xTF32 splits by truncation: its biased dropped terms add up over the 36 864 - 147 456 pixel sum; the step
+            # runs these shapes in 3xFP16)
+            for mode, tol in (("1", 1e-4), ("0", 4e-4)):
                 got = res[mode][2][r, sx][ci.cpu()]
                 err = float((got - ref).abs().max() / ref.abs().max())
                 assert err <= tol, f"NVAE_F16X3={mode}: dw tap ({r},{sx}) vs float64: {err:.2e}"
@@ -629,3 +631,43 @@ def test_philox_normal_moments_and_streams(rt):
     c = rt.empty(1 << 20)
     rt.lib.philox_normal(c.data_ptr(), c.numel(), 1234, None, 0, rt.stream)
     assert torch.equal(a, c)  # counter-based: reproducible
+
+
+@pytest.mark.parametrize("shape", [(144, 16, 16, 384, 384), (144, 32, 32, 192, 192), (144, 16, 16, 64, 384)])
+def test_large_convolutions_are_bitwise_repeatable(lib_built, shape, monkeypatch):
+    """Forward, backward-data and backward-filter of the step's large GEMMs, 30 launches back to back with the workspace
+    scrambled in between, must give bit-identical results: split-K partials are summed in a fixed order and nothing may
+    depend on what the workspace held or on kernel timing.  (Round 2: this caught the N = 384 backward-filter reading a
+    tile that had not landed -- TMEM A ring one slot deeper than the shared-memory ring -- in ~1 launch of 13.)"""
+    import ctypes as C
+    from nvae_tf_b200 import _lib
+    from nvae_tf_b200 import runtime as R
+    from nvae_tf_b200.layers import Conv2D
+    monkeypatch.delenv("NVAE_F16X3_MIN_GFLOP", raising=False)
+    N, Hh, W, Cin, Cout = shape
+    k = 5 if Cin == Cout else 1
+    g = torch.Generator(device="cpu").manual_seed(5)
+    with R.Runtime(seed=7, precision=_lib.NVAE_PREC_TF32X3) as rt:
+        conv = Conv2D(Cout, (k, k), padding="same", in_channels=Cin, name="c")
+        rt.finalize()
+        rt.pack_plain(conv)
+        x = torch.randn(N, Hh, W, Cin, generator=g).to(rt.device)
+        dy = (torch.randn(N, Hh, W, Cout, generator=g) * 1e-3).to(rt.device)
+        d = R.conv_desc(rt, tuple(x.shape), 0, conv.kernel.shape, 1)
+        ws, wsb = rt.workspace(max(rt.lib._nvae_conv2d_ws_bytes(C.byref(d), i) for i in range(3)))
+        y, dx = torch.empty(N, Hh, W, Cout, device=rt.device), torch.empty(N, Hh, W, Cin, device=rt.device)
+        ref = None
+        for rep in range(30):
+            rt._ws["main"].random_(0, 255)
+            rt.lib.conv2d_fwd(C.byref(d), x.data_ptr(), None, conv.kernel.ptr(), conv.packed_fwd(), None, None, y.data_ptr(),
+                              ws, wsb, rt.stream)
+            rt.lib.conv2d_dgrad(C.byref(d), dy.data_ptr(), conv.kernel.ptr(), conv.packed_dgrad(), dx.data_ptr(), None, 0, ws,
+                                wsb, rt.stream)
+            rt.lib.conv2d_wgrad(C.byref(d), x.data_ptr(), None, dy.data_ptr(), conv.kernel.gptr(), None, ws, wsb, rt.stream)
+            out = (y.clone(), dx.clone(), conv.kernel.grad.clone())
+            if ref is None:
+                ref = out
+            else:
+                for name, a, b in zip(("y", "dx", "dw"), ref, out):
+                    assert torch.equal(a, b), f"{name} differs on launch {rep}"
+        torch.cuda.synchronize()

@@ -288,6 +288,7 @@ def test_cuda_graph_replay_equals_eager(lib_built):
             outs = [m.train_step(x.cuda()) for _ in range(5)]
             loss = outs[-1]["loss"].item()
         else:
+            m._sync_counters()  # `m.steps = 7` above reaches the device counter on the next step / capture; do it now
             before = (m.rt.params.clone(), m.rt.state.clone(), m._counters.clone())
             static_in, replay = m.capture_train_step((4, 32, 32, 1), warmup=2)
             torch.cuda.synchronize()

@@ -22,12 +22,24 @@ B = 144
 TOL = 1e-3
 
 
-def _model(precision=None, seed=1):
+GAMMA = 0.3
+
+
+def _model(precision=None, seed=1, gamma=GAMMA):
+    """Default-config model at the operating point the parity bound is meaningful at.  With Keras' initial gamma = 1 the
+    untrained network is numerically chaotic at batch 144: sigma = exp(softclamp5(.)) saturates at e^5 = 148, z reaches
+    +-300, and ANY two fp32 implementations disagree at the 1e-3 level -- torch-CPU fp32 vs the float64 oracle on this very
+    step: logits 7.6e-4, kl_all 3.2e-4 (tools/conditioning_probe.py).  With every BN gamma at 0.3 -- where the BN-gamma
+    regulariser of models.py:252-267 drives a trained model -- the same comparison gives logits 8e-7, kl_all 5e-7, so a
+    1e-3 bound tests the arithmetic rather than the conditioning of a random network."""
     from nvae_tf_b200.models import NVAE, Adamax, CosineDecay
     cfg = O.NVAEConfig()
     m = NVAE(**H.mirror_kwargs(cfg, B), training=True, precision=precision, seed=seed)
     m.compile(optimizer=Adamax(learning_rate=CosineDecay(1e-3, 400 * 417)), run_eagerly=True)
     m.steps = 20000  # inside the KL warm-up: beta < 1, balancing on (what bench.py runs)
+    for v in m.rt.variables.values():
+        if v.name.endswith("/gamma"):
+            v.value.mul_(gamma)
     return m
 
 
@@ -100,10 +112,11 @@ def test_batch144_losses_match_float64_oracle(lib_built, monkeypatch):
     monkeypatch.delenv("NVAE_F16X3_MIN_GFLOP", raising=False)
     cfg = O.NVAEConfig()
     params, trainable, bnl, s = O.build_params(cfg, seed=1, jitter=0.05)
-    params = {k: np.asarray(v, np.float32).astype(np.float64) for k, v in params.items()}
+    params = {k: np.asarray(v * (GAMMA if k.endswith("/gamma") else 1.0), np.float32).astype(np.float64)
+              for k, v in params.items()}
     x = _images(2).numpy()
     eps = [np.asarray(e.numpy(), np.float32).astype(np.float64) for e in O.make_eps(s, B, seed=2)]
-    m = _model()
+    m = _model(gamma=1.0)
     m.rt.load_named(params)
     m.rt.inject_eps(eps)
     out = m.train_step(x, apply_gradients=False)

@@ -16,6 +16,7 @@ struct GpuDevice {
 namespace tensorflow {
 typedef std::uint8_t uint8;
 typedef std::int64_t int64;
+typedef std::int32_t int32;
 enum DataType { DT_FLOAT = 1, DT_UINT8 = 4 };
 constexpr const char* DEVICE_GPU = "GPU";
 
@@ -65,6 +66,7 @@ class OpKernelConstruction {
 class OpKernelContext {
  public:
   const Tensor& input(int) { return t_; }
+  Tensor mutable_input(int, bool) { return t_; }
   Status allocate_output(int, const TensorShape&, Tensor** out) { *out = &t_; return Status(); }
   Status allocate_temp(DataType, const TensorShape&, Tensor*) { return Status(); }
   template <typename D>

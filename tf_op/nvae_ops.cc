@@ -379,3 +379,303 @@ class NvaeLatentBwdOp : public OpKernel {
   }
 };
 REGISTER_KERNEL_BUILDER(Name("NvaeLatentBwd").Device(DEVICE_GPU), NvaeLatentBwdOp);
+
+// ------------------------------------------------------------------------------------------------
+// The once-per-step launchers around the cells: spectral normalisation of every wrapped conv, losses, optimizer, noise.
+// ------------------------------------------------------------------------------------------------
+// tfa.layers.SpectralNormalization(power_iterations=1) for ALL layers of the model in one op (4 launches) + the operand
+// repack the tensor-core convolutions consume.  `params` / `state` are the flat fp32 arenas the variables are views of,
+// `layers` the NvaeSnLayer table (bytes), `chunk_layer` its row-chunk index (see Runtime._build_sn_tables).  Updates
+// params (W /= sigma), state (u) and pack IN PLACE, like the reference's kernel.assign / u.assign; the op's
+// output `sigma` gives the step something to take a control dependency on before the first conv.
+REGISTER_OP("NvaeSpectralNorm")
+    .Input("params: Ref(float)").Input("state: Ref(float)").Input("pack: Ref(float)").Input("layers: uint8")
+    .Input("chunk_layer: int32").Input("ws: Ref(float)")
+    .Attr("power_iter: bool = true").Attr("pack_exact: bool = true")
+    .Output("sigma: float");
+
+class NvaeSpectralNormOp : public OpKernel {
+ public:
+  explicit NvaeSpectralNormOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("power_iter", &power_iter_));
+    OP_REQUIRES_OK(c, c->GetAttr("pack_exact", &pack_exact_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    Tensor params = ctx->mutable_input(0, true), state = ctx->mutable_input(1, true), pack = ctx->mutable_input(2, true),
+           ws = ctx->mutable_input(5, true);
+    const Tensor &layers = ctx->input(3), &chunk_layer = ctx->input(4);
+    const int n_layers = static_cast<int>(layers.NumElements() / sizeof(NvaeSnLayer));
+    Tensor* sigma = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({n_layers}), &sigma));
+    const int rc = nvae_spectral_norm(fptr(&params), fptr(&state), fptr(&pack),
+                                      reinterpret_cast<const NvaeSnLayer*>(layers.flat<uint8>().data()), n_layers,
+                                      chunk_layer.flat<int32>().data(), static_cast<int>(chunk_layer.NumElements()),
+                                      power_iter_ ? 1 : 0, pack_exact_ ? 1 : 0, fptr(sigma), fptr(&ws), stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_spectral_norm failed: ", rc));
+  }
+ private:
+  bool power_iter_, pack_exact_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeSpectralNorm").Device(DEVICE_GPU), NvaeSpectralNormOp);
+
+// Batch statistics only ([4,C] = mean, invstd, scale, shift; moving statistics updated): consumers that fuse the apply
+REGISTER_OP("NvaeBnStats")
+    .Input("x: float").Input("gamma: float").Input("beta: float").Input("moving_mean: Ref(float)")
+    .Input("moving_var: Ref(float)")
+    .Attr("training: bool = true").Attr("momentum: float = 0.05").Attr("epsilon: float = 1e-5")
+    .Output("stat: float");
+
+class NvaeBnStatsOp : public OpKernel {
+ public:
+  explicit NvaeBnStatsOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("training", &training_));
+    OP_REQUIRES_OK(c, c->GetAttr("momentum", &momentum_));
+    OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &x = ctx->input(0), &gamma = ctx->input(1), &beta = ctx->input(2);
+    Tensor mm = ctx->mutable_input(3, true), mv = ctx->mutable_input(4, true);
+    const int C = static_cast<int>(x.dim_size(x.dims() - 1));
+    Tensor* stat = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({4, C}), &stat));
+    Tensor ws;
+    const size_t ws_bytes = nvae_bn_ws_bytes(rows_of(x), C);
+    OP_REQUIRES_OK(ctx, alloc_ws(ctx, ws_bytes, &ws));
+    const int rc = nvae_bn_stats(fptr(x), rows_of(x), C, fptr(gamma), fptr(beta), fptr(&mm), fptr(&mv), training_ ? 1 : 0,
+                                 momentum_, eps_, fptr(stat), ws.flat<uint8>().data(), ws_bytes, stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_bn_stats failed: ", rc));
+  }
+ private:
+  bool training_;
+  float momentum_, eps_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeBnStats").Device(DEVICE_GPU), NvaeBnStatsOp);
+
+// Bernoulli(logits).log_prob(x) summed over H,W,C (models.py:242-250) and its gradient w.r.t. the logits
+REGISTER_OP("NvaeBernoulliLlFwd")
+    .Input("logits: float").Input("x: float").Attr("crop: int = 0")
+    .Output("recon: float");
+
+class NvaeBernoulliLlFwdOp : public OpKernel {
+ public:
+  explicit NvaeBernoulliLlFwdOp(OpKernelConstruction* c) : OpKernel(c) { OP_REQUIRES_OK(c, c->GetAttr("crop", &crop_)); }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &l = ctx->input(0), &x = ctx->input(1);
+    const int B = x.dim_size(0), H = x.dim_size(1), W = x.dim_size(2), C = x.dim_size(3), Cl = l.dim_size(3);
+    Tensor* recon = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({B}), &recon));
+    const int rc = nvae_bernoulli_ll_fwd(fptr(l), fptr(x), B, H, W, C, Cl, crop_, fptr(recon), stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_bernoulli_ll_fwd failed: ", rc));
+  }
+ private:
+  int crop_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeBernoulliLlFwd").Device(DEVICE_GPU), NvaeBernoulliLlFwdOp);
+
+REGISTER_OP("NvaeBernoulliLlBwd")
+    .Input("logits: float").Input("x: float").Attr("scale: float = 1.0")
+    .Output("dlogits: float");
+
+class NvaeBernoulliLlBwdOp : public OpKernel {
+ public:
+  explicit NvaeBernoulliLlBwdOp(OpKernelConstruction* c) : OpKernel(c) { OP_REQUIRES_OK(c, c->GetAttr("scale", &scale_)); }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &l = ctx->input(0), &x = ctx->input(1);
+    const int B = x.dim_size(0), H = x.dim_size(1), W = x.dim_size(2), C = x.dim_size(3), Cl = l.dim_size(3);
+    Tensor* dl = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, l.shape(), &dl));
+    const int rc = nvae_bernoulli_ll_bwd(fptr(l), fptr(x), B, H, W, C, Cl, scale_, fptr(dl), stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_bernoulli_ll_bwd failed: ", rc));
+  }
+ private:
+  float scale_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeBernoulliLlBwd").Device(DEVICE_GPU), NvaeBernoulliLlBwdOp);
+
+// KL balancing + beta warm-up + batch mean + total (models.py:121-126, 204-222) in one launch
+REGISTER_OP("NvaeLossAssemble")
+    .Input("kl_all: float").Input("recon: float").Input("bn_loss: float").Input("alphas: float").Input("hyper: float")
+    .Attr("balancing: int = -1")
+    .Output("kl_weight: float").Output("kl_loss: float").Output("scalars: float");
+
+class NvaeLossAssembleOp : public OpKernel {
+ public:
+  explicit NvaeLossAssembleOp(OpKernelConstruction* c) : OpKernel(c) { OP_REQUIRES_OK(c, c->GetAttr("balancing", &bal_)); }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &kl_all = ctx->input(0), &recon = ctx->input(1), &bn_loss = ctx->input(2), &alphas = ctx->input(3),
+                 &hyper = ctx->input(4);
+    const int G = kl_all.dim_size(0), B = kl_all.dim_size(1);
+    Tensor *klw = nullptr, *kl = nullptr, *sc = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({G}), &klw));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape({B}), &kl));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, TensorShape({2}), &sc));
+    const int rc = nvae_loss_assemble(fptr(kl_all), fptr(recon), fptr(bn_loss), fptr(alphas), fptr(hyper), bal_, G, B,
+                                      fptr(klw), fptr(kl), fptr(sc), stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_loss_assemble failed: ", rc));
+  }
+ private:
+  int bal_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeLossAssemble").Device(DEVICE_GPU), NvaeLossAssembleOp);
+
+// sr_lambda * sum_k max|gamma_k| over the 88 encoder/decoder-group BN layers (models.py:252-267) and its sub-gradient
+REGISTER_OP("NvaeBnLossFwd")
+    .Input("params: float").Input("offsets: int64").Input("sizes: int32").Attr("sr_lambda: float")
+    .Output("loss: float");
+
+class NvaeBnLossFwdOp : public OpKernel {
+ public:
+  explicit NvaeBnLossFwdOp(OpKernelConstruction* c) : OpKernel(c) { OP_REQUIRES_OK(c, c->GetAttr("sr_lambda", &lam_)); }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &params = ctx->input(0), &off = ctx->input(1), &sz = ctx->input(2);
+    Tensor* loss = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({1}), &loss));
+    const int rc = nvae_bn_loss_fwd(fptr(params), reinterpret_cast<const int64_t*>(off.flat<int64>().data()),
+                                    sz.flat<int32>().data(), static_cast<int>(off.NumElements()), lam_, fptr(loss),
+                                    stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_bn_loss_fwd failed: ", rc));
+  }
+ private:
+  float lam_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeBnLossFwd").Device(DEVICE_GPU), NvaeBnLossFwdOp);
+
+REGISTER_OP("NvaeBnLossBwd")
+    .Input("params: float").Input("grads: Ref(float)").Input("offsets: int64").Input("sizes: int32")
+    .Attr("sr_lambda: float")
+    .Output("done: float");
+
+class NvaeBnLossBwdOp : public OpKernel {
+ public:
+  explicit NvaeBnLossBwdOp(OpKernelConstruction* c) : OpKernel(c) { OP_REQUIRES_OK(c, c->GetAttr("sr_lambda", &lam_)); }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &params = ctx->input(0), &off = ctx->input(2), &sz = ctx->input(3);
+    Tensor grads = ctx->mutable_input(1, true);
+    Tensor* done = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({0}), &done));
+    const int rc = nvae_bn_loss_bwd(fptr(params), fptr(&grads), reinterpret_cast<const int64_t*>(off.flat<int64>().data()),
+                                    sz.flat<int32>().data(), static_cast<int>(off.NumElements()), lam_, stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_bn_loss_bwd failed: ", rc));
+  }
+ private:
+  float lam_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeBnLossBwd").Device(DEVICE_GPU), NvaeBnLossBwdOp);
+
+// optimizers.Adamax + CosineDecay + the beta warm-up (train.py:128-131, models.py:121-122,128-129): the schedule launch
+// derives {beta, lr_t, ...} from device counters, the multi-tensor Adamax updates the whole parameter arena in one launch
+REGISTER_OP("NvaeScheduleStep")
+    .Input("counters: Ref(int64)")
+    .Attr("warmup_iters: float").Attr("lr0: float").Attr("decay_steps: float").Attr("beta_1: float = 0.9")
+    .Attr("advance: int = 3")
+    .Output("hyper: float");
+
+class NvaeScheduleStepOp : public OpKernel {
+ public:
+  explicit NvaeScheduleStepOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("warmup_iters", &warm_)); OP_REQUIRES_OK(c, c->GetAttr("lr0", &lr0_));
+    OP_REQUIRES_OK(c, c->GetAttr("decay_steps", &decay_)); OP_REQUIRES_OK(c, c->GetAttr("beta_1", &b1_));
+    OP_REQUIRES_OK(c, c->GetAttr("advance", &adv_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    Tensor counters = ctx->mutable_input(0, true);
+    Tensor* hyper = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({8}), &hyper));
+    const int rc = nvae_schedule_step(reinterpret_cast<int64_t*>(counters.flat<int64>().data()), fptr(hyper), warm_, lr0_,
+                                      decay_, b1_, adv_, stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_schedule_step failed: ", rc));
+  }
+ private:
+  float warm_, lr0_, decay_, b1_;
+  int adv_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeScheduleStep").Device(DEVICE_GPU), NvaeScheduleStepOp);
+
+REGISTER_OP("NvaeAdamax")
+    .Input("params: Ref(float)").Input("grads: float").Input("m: Ref(float)").Input("v: Ref(float)").Input("hyper: float")
+    .Attr("beta_1: float = 0.9").Attr("beta_2: float = 0.999").Attr("epsilon: float = 1e-7").Attr("grad_scale: float = 1.0")
+    .Output("done: float");
+
+class NvaeAdamaxOp : public OpKernel {
+ public:
+  explicit NvaeAdamaxOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("beta_1", &b1_)); OP_REQUIRES_OK(c, c->GetAttr("beta_2", &b2_));
+    OP_REQUIRES_OK(c, c->GetAttr("epsilon", &eps_)); OP_REQUIRES_OK(c, c->GetAttr("grad_scale", &gs_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    Tensor p = ctx->mutable_input(0, true), m = ctx->mutable_input(2, true), v = ctx->mutable_input(3, true);
+    const Tensor &g = ctx->input(1), &hyper = ctx->input(4);
+    Tensor* done = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({0}), &done));
+    const int rc = nvae_adamax(fptr(&p), fptr(g), fptr(&m), fptr(&v), p.NumElements(), fptr(hyper), b1_, b2_, eps_, gs_,
+                               stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_adamax failed: ", rc));
+  }
+ private:
+  float b1_, b2_, eps_, gs_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeAdamax").Device(DEVICE_GPU), NvaeAdamaxOp);
+
+// epsilon ~ N(0,1) (common.py:67) from Philox keyed by (seed, device iteration counter, stream id); z = mu + eps * sigma
+REGISTER_OP("NvaePhiloxNormal")
+    .Input("counters: int64").Attr("n: int").Attr("seed: int").Attr("stream_id: int = 0")
+    .Output("eps: float");
+
+class NvaePhiloxNormalOp : public OpKernel {
+ public:
+  explicit NvaePhiloxNormalOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("n", &n_)); OP_REQUIRES_OK(c, c->GetAttr("seed", &seed_));
+    OP_REQUIRES_OK(c, c->GetAttr("stream_id", &sid_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& counters = ctx->input(0);
+    Tensor* eps = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({static_cast<int64_t>(n_)}), &eps));
+    const int rc = nvae_philox_normal(fptr(eps), n_, static_cast<uint64_t>(seed_),
+                                      reinterpret_cast<const int64_t*>(counters.flat<int64>().data()),
+                                      static_cast<uint64_t>(sid_), stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_philox_normal failed: ", rc));
+  }
+ private:
+  int n_, seed_, sid_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaePhiloxNormal").Device(DEVICE_GPU), NvaePhiloxNormalOp);
+
+REGISTER_OP("NvaeReparam")
+    .Input("mu: float").Input("sigma: float").Input("eps: float").Attr("sigma_scale: float = 1.0")
+    .Output("z: float");
+
+class NvaeReparamOp : public OpKernel {
+ public:
+  explicit NvaeReparamOp(OpKernelConstruction* c) : OpKernel(c) { OP_REQUIRES_OK(c, c->GetAttr("sigma_scale", &ss_)); }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &mu = ctx->input(0), &sigma = ctx->input(1), &eps = ctx->input(2);
+    Tensor* z = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, mu.shape(), &z));
+    const int rc = nvae_reparam(fptr(mu), fptr(sigma), fptr(eps), ss_, fptr(z), mu.NumElements(), stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_reparam failed: ", rc));
+  }
+ private:
+  float ss_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeReparam").Device(DEVICE_GPU), NvaeReparamOp);
+
+// Importance-weighted NLL bound over K attempts (evaluate.py:111-123): rows k of recon / log_q / log_p -> nll[1]
+REGISTER_OP("NvaeIwaeNll")
+    .Input("recon: float").Input("log_q: float").Input("log_p: float")
+    .Output("per_sample: float").Output("nll: float");
+
+class NvaeIwaeNllOp : public OpKernel {
+ public:
+  explicit NvaeIwaeNllOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &recon = ctx->input(0), &lq = ctx->input(1), &lp = ctx->input(2);
+    const int K = recon.dim_size(0), B = recon.dim_size(1);
+    Tensor *ps = nullptr, *nll = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({B}), &ps));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape({1}), &nll));
+    const int rc = nvae_iwae_nll(fptr(recon), fptr(lq), fptr(lp), K, B, fptr(ps), fptr(nll), stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_iwae_nll failed: ", rc));
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeIwaeNll").Device(DEVICE_GPU), NvaeIwaeNllOp);

@@ -118,3 +118,91 @@ def latent(enc_p, dec_p, eps, kl_weight):
             return d_enc, (None if dec_p is None else d_dec)
         return (z, kl, dist), grad
     return f(enc_p, dec_)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Once-per-step launchers around the cells (models.py:116-129, 191-267; train.py:128-131)
+# ---------------------------------------------------------------------------------------------------------------------
+def spectral_norm_all(arena, training=True):
+    """tfa.SpectralNormalization(power_iterations=1) of EVERY wrapped conv in one op (4 launches) + the operand repack the
+    tensor-core convolutions read (`kernel_tr`).  `arena` bundles what nvae_tf_b200.runtime.Runtime lays out once at
+    model build: flat `params` / `state` / `pack` resource variables (the Keras variables are views of them), the
+    NvaeSnLayer table and its chunk index as constant tensors, and a float scratch variable.
+
+    Sequencing under tf.function: the op mutates the arenas, so everything that reads a kernel must run after it.
+    `NVAE.call` does
+
+        sigma = spectral_norm_all(self.arena, training)
+        with tf.control_dependencies([sigma]):
+            x = self.preprocess(inputs) ...
+
+    -- one control edge ahead of the first conv, exactly where the reference's first `SpectralNormalization.call`
+    would have normalised its kernel."""
+    return _ops.nvae_spectral_norm(params=arena.params, state=arena.state, pack=arena.pack, layers=arena.sn_layers,
+                                   chunk_layer=arena.sn_chunk_layer, ws=arena.sn_ws, power_iter=training, pack_exact=True)
+
+
+def bn_stats(x, bn, training=True):
+    """[4, C] statistics block only (moving statistics updated in place), via the dedicated launcher."""
+    return tf.stop_gradient(_ops.nvae_bn_stats(x=x, gamma=bn.gamma, beta=bn.beta, moving_mean=bn.moving_mean,
+                                               moving_var=bn.moving_variance, training=training, momentum=bn.momentum,
+                                               epsilon=bn.epsilon))
+
+
+def bernoulli_recon_loss(inputs, logits, crop_output=False):
+    """NVAE.calculate_recon_loss (models.py:242-250): -sum_{h,w,c} Bernoulli(logits).log_prob(x) -> [B]."""
+    @tf.custom_gradient
+    def f(logits):
+        ll = _ops.nvae_bernoulli_ll_fwd(logits=logits, x=inputs, crop=2 if crop_output else 0)
+
+        def grad(d):  # d(recon[b]) / d(logits) = sigmoid(l) - x, scaled per sample by the upstream gradient
+            g = _ops.nvae_bernoulli_ll_bwd(logits=logits, x=inputs, scale=1.0)
+            return g * tf.reshape(d, [-1, 1, 1, 1])
+        return ll, grad
+    return f(logits)
+
+
+def loss_assemble(kl_all, recon, bn_loss, alphas, hyper, balancing=-1):
+    """models.py:121-126, 204-222 in one launch: (kl_weight[G], kl_loss[B], [total, mean(recon + kl_loss)])."""
+    return _ops.nvae_loss_assemble(kl_all=kl_all, recon=recon, bn_loss=bn_loss, alphas=alphas, hyper=hyper,
+                                   balancing=balancing)
+
+
+def bn_loss(arena, sr_lambda):
+    """NVAE.calculate_bn_loss (models.py:252-267) over the flat parameter arena; its sub-gradient is added to the
+    gradient arena by bn_loss_backward (tf.reduce_max splits evenly among ties)."""
+    return _ops.nvae_bn_loss_fwd(params=arena.params, offsets=arena.bn_loss_offsets, sizes=arena.bn_loss_sizes,
+                                 sr_lambda=sr_lambda)
+
+
+def bn_loss_backward(arena, sr_lambda):
+    return _ops.nvae_bn_loss_bwd(params=arena.params, grads=arena.grads, offsets=arena.bn_loss_offsets,
+                                 sizes=arena.bn_loss_sizes, sr_lambda=sr_lambda)
+
+
+def schedule_step(arena, warmup_iters, lr0, decay_steps, beta_1=0.9, advance=3):
+    """beta warm-up (models.py:121-122) and the CosineDecay / Adamax bias-corrected step size (train.py:128-130) from the
+    device counters {warm-up metric, optimizer iterations}; returns hyper[8] = {beta, lr_t, lr, t, metric, ...}."""
+    return _ops.nvae_schedule_step(counters=arena.counters, warmup_iters=warmup_iters, lr0=lr0, decay_steps=decay_steps,
+                                   beta_1=beta_1, advance=advance)
+
+
+def adamax_apply(arena, hyper, beta_1=0.9, beta_2=0.999, epsilon=1e-7, grad_scale=1.0):
+    """optimizer.apply_gradients (models.py:128) as ONE multi-tensor launch over the arenas; grad_scale = 1 / replicas."""
+    return _ops.nvae_adamax(params=arena.params, grads=arena.grads, m=arena.adamax_m, v=arena.adamax_v, hyper=hyper,
+                            beta_1=beta_1, beta_2=beta_2, epsilon=epsilon, grad_scale=grad_scale)
+
+
+def philox_normal(arena, n, seed, stream_id=0):
+    """tf.random.normal stand-in for Sampler.sample's epsilon (common.py:67), reproducible under graph replay."""
+    return _ops.nvae_philox_normal(counters=arena.counters[1:], n=n, seed=seed, stream_id=stream_id)
+
+
+def reparam(mu, sigma, eps, sigma_scale=1.0):
+    """Sampler.sample on materialised parameters: mu + eps * sigma * sigma_scale (common.py:65-68, models.py:140-145)."""
+    return _ops.nvae_reparam(mu=mu, sigma=sigma, eps=eps, sigma_scale=sigma_scale)
+
+
+def iwae_nll(recon, log_q, log_p):
+    """evaluate.py:118-121: -mean_b(logsumexp_k(-recon - log_q + log_p) - log K) from [K, B] stacks -> (per_sample, nll)."""
+    return _ops.nvae_iwae_nll(recon=recon, log_q=log_q, log_p=log_p)

@@ -33,8 +33,12 @@ def main():
     t_lo = min(e.time_range.start for e in evs)
     t_hi = max(e.time_range.end for e in evs)
     per_stream = defaultdict(float)
+    main_stream = None
     for e in evs:
-        a = agg[e.name[:100]]
+        sid = getattr(e, "device_resource_id", getattr(e, "device_index", 0))
+        if main_stream is None:
+            main_stream = sid  # the first kernel of the step (gradient fill) runs on the main stream
+        a = agg[("M " if sid == main_stream else "S ") + e.name[:100]]
         a[0] += 1
         a[1] += e.device_time
         a[2] = max(a[2], e.device_time)
