@@ -93,6 +93,19 @@ __device__ __forceinline__ double dsmem_ld_f64(const double* local, unsigned ran
   return v;
 }
 
+__device__ __forceinline__ float dsmem_ld_f32(const float* local, unsigned rank) {
+  float v;
+  asm volatile(
+      "{\n\t.reg .u32 la, ra;\n\t"
+      "cvt.u32.u64 la, %1;\n\t"
+      "mapa.shared::cluster.u32 ra, la, %2;\n\t"
+      "ld.shared::cluster.f32 %0, [ra];\n\t}"
+      : "=f"(v)
+      : "l"(__cvta_generic_to_shared(local)), "r"(rank)
+      : "memory");
+  return v;
+}
+
 // ---- activations -------------------------------------------------------------
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float u) {
@@ -158,6 +171,20 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // ---- 128-bit streaming access -----------------------------------------------------------------
+// "Last block finalizes": after a CTA has written its partial results, one thread takes a ticket; the CTA that draws
+// the last ticket of its group knows every partial is in L2 (fence before the ticket, fence after) and does the
+// combine -- in a FIXED order over the partials, so the result does not depend on which CTA came last.  No CTA ever waits
+// for another one (no co-residency assumption, no deadlock).  `ticket` must be zero at launch (a memset node ahead of it).
+__device__ __forceinline__ bool last_block_of(unsigned* ticket, unsigned group_size) {
+  __shared__ unsigned s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == group_size - 1u;
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void stg4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 

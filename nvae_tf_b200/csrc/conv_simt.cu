@@ -197,32 +197,39 @@ __global__ void __launch_bounds__(kSimtThreads) simt_conv_kernel(const Prob p, i
     for (int j = 0; j < 4; ++j) p.store(m0 + ty * 4 + i, n0 + tx * 4 + j, acc[i][j]);
 }
 
-// column sums of a [rows, C] matrix, deterministic two-stage
-__global__ void colsum_partial_kernel(const float* __restrict__ a, int64_t rows, int C, int ld, int64_t rows_per_split,
-                                      float* __restrict__ part) {
+// column sums of a [rows, C] matrix (bias gradient): each CTA sums a row range of 32 columns into part[split][C]; the last
+// CTA of a column chunk to finish (ticket[blockIdx.x], zeroed ahead of the launch) adds the chunk's partials in split order --
+// deterministic, one launch
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ a, int64_t rows, int C, int ld,
+                                                     int64_t rows_per_split, float* __restrict__ part,
+                                                     unsigned* __restrict__ ticket, float* __restrict__ out) {
   nvae::pdl_enter();
   __shared__ float sm[8][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
   const int64_t r1 = r0 + rows_per_split < rows ? r0 + rows_per_split : rows;
-  float s = 0.f;
-  if (c < C)
-    for (int64_t r = r0 + ry; r < r1; r += 8) s += __ldg(a + r * ld + c);
-  sm[ry][threadIdx.x & 31] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < C) {
+    int64_t r = r0 + ry;
+    for (; r + 24 < r1; r += 32) {  // four independent loads in flight, fixed association
+      s0 += __ldg(a + r * ld + c); s1 += __ldg(a + (r + 8) * ld + c);
+      s2 += __ldg(a + (r + 16) * ld + c); s3 += __ldg(a + (r + 24) * ld + c);
+    }
+    for (; r < r1; r += 8) s0 += __ldg(a + r * ld + c);
+  }
+  sm[ry][threadIdx.x & 31] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (ry == 0 && c < C) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
     part[(int64_t)blockIdx.y * C + c] = t;
   }
-}
-__global__ void colsum_final_kernel(const float* __restrict__ part, int nsplit, int C, float* __restrict__ out) {
-  nvae::pdl_enter();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f;
-  for (int i = 0; i < nsplit; ++i) s += part[(int64_t)i * C + c];
-  out[c] = s;
+  if (!last_block_of(ticket + blockIdx.x, gridDim.y)) return;
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+    for (int i = 0; i < (int)gridDim.y; ++i) t += __ldcg(part + (int64_t)i * C + c);
+    out[c] = t;
+  }
 }
 
 }  // namespace nvae
@@ -258,16 +265,17 @@ int nvae_colsum(const float* a, int64_t rows, int C, int ld, float* out, void* w
   if (nsplit > 256) nsplit = 256;
   const int64_t rps = ceil_div(rows, nsplit);
   nsplit = ceil_div(rows, rps);
-  if (ws == nullptr || ws_bytes < (size_t)nsplit * C * sizeof(float)) return NVAE_E_WORKSPACE;
+  const int nchunk = (C + 31) / 32;
+  if (ws == nullptr || ws_bytes < (size_t)nsplit * C * sizeof(float) + (size_t)nchunk * sizeof(unsigned)) return NVAE_E_WORKSPACE;
   float* part = reinterpret_cast<float*>(ws);
-  nvae::launch(colsum_partial_kernel, dim3((C + 31) / 32, (unsigned)nsplit), 256, 0, stream, a, rows, C, ld, rps, part);
-  NVAE_RETURN_IF_LAUNCH_FAILED();
-  nvae::launch(colsum_final_kernel, (C + 127) / 128, 128, 0, stream, part, (int)nsplit, C, out);
+  unsigned* ticket = reinterpret_cast<unsigned*>(part + (size_t)nsplit * C);
+  NVAE_CUDA_TRY(cudaMemsetAsync(ticket, 0, (size_t)nchunk * sizeof(unsigned), stream));
+  nvae::launch(colsum_kernel, dim3(nchunk, (unsigned)nsplit), 256, 0, stream, a, rows, C, ld, rps, part, ticket, out);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
 
-size_t nvae_colsum_ws_bytes(int C) { return (size_t)256 * C * sizeof(float); }
+size_t nvae_colsum_ws_bytes(int C) { return (size_t)256 * C * sizeof(float) + (size_t)((C + 31) / 32) * sizeof(unsigned); }
 
 // Cout == 1 head (postprocess.py:29): y[pix] = b + sum_{tap,c} x[pix+tap][c] * w[tap][c].  Bandwidth-shaped, not
 // GEMM-shaped: 8 lanes share a pixel (coalesced 128-byte channel rows), taps come from L1, a 3-step shuffle sums them.

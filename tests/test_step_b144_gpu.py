@@ -105,7 +105,10 @@ def test_batch144_graph_replay_matches_fp32_cuda_core_path(lib_built, monkeypatc
           "median %.2e over %d tensors" % (errs[len(errs) // 2][0], len(errs)))
     assert errs[0][0] <= TOL, errs[:5]
     for n, off, size in snames:  # BN moving statistics, SN u
-        assert _rel(state_tc[off:off + size], state_32[off:off + size], 1e-6) <= TOL, n
+        # (a conv with zero bias behind a zero-mean BN output has an analytically zero channel mean: its moving_mean is
+        # round-off, ~1e-9 against activations of order 1 -- hence the absolute floor for the means)
+        floor = 1e-3 if n.endswith("moving_mean") else 1e-6
+        assert _rel(state_tc[off:off + size], state_32[off:off + size], floor) <= TOL, n
 
 
 def test_batch144_losses_match_float64_oracle(lib_built, monkeypatch):
