@@ -77,56 +77,10 @@ __device__ __forceinline__ void bn_block_reduce(float4& s, float4& q, int LC, fl
   }
 }
 
-// Combine of the per-CTA (mean, M2) partials of ONE channel by one warp: lane l takes splits l, l+32, ...; plain sums
-// (mean = sum n_s*m_s / n;  M2 = sum q_s + n_s*m_s^2 - n*mean^2 -- the partials are fp64 and pivot-shifted, so the textbook
-// form has bits to spare) and a fixed shuffle tree: deterministic.  Writes stat[4][C] and the moving statistics.
-__device__ __forceinline__ void bn_finalize_channel(const double* part, int nsplit, int64_t rows, int64_t rows_per_split,
-                                                    int C, int c, const float* gamma, const float* beta, float* mm, float* mv,
-                                                    float momentum, float eps, float* stat) {
-  const int lane = threadIdx.x & 31;
-  const double n = (double)rows;
-  const double n_last = (double)(rows - (int64_t)(nsplit - 1) * rows_per_split), n_full = (double)rows_per_split;
-  double a0 = 0, a1 = 0, a2 = 0;
-#pragma unroll 4
-  for (int s = lane; s < nsplit; s += 32) {
-    const double ns = s == nsplit - 1 ? n_last : n_full;
-    const double m = __ldcg(part + ((int64_t)s * 2) * C + c), q = __ldcg(part + ((int64_t)s * 2 + 1) * C + c);
-    a0 += ns * m;
-    a1 += q;
-    a2 += ns * m * m;
-  }
-  a0 = warp_sum(a0);
-  a1 = warp_sum(a1);
-  a2 = warp_sum(a2);
-  if (lane != 0) return;
-  const double mu = a0 / n;
-  double M2 = a1 + a2 - n * mu * mu;
-  if (M2 < 0) M2 = 0;
-  const float mean = (float)mu, var = (float)(M2 / n);
-  if (mm != nullptr) {
-    const double unbiased = n > 1 ? M2 / (n - 1) : M2 / n;
-    mm[c] = mm[c] * momentum + mean * (1.f - momentum);
-    mv[c] = mv[c] * momentum + (float)unbiased * (1.f - momentum);
-  }
-  const float invstd = rsqrtf(var + eps);
-  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-  const float scale = g * invstd;
-  stat[c] = mean;
-  stat[C + c] = invstd;
-  stat[2 * C + c] = scale;
-  stat[3 * C + c] = b - mean * scale;
-}
-
-// part: [nsplit][2][C] doubles (mean, M2) using a per-CTA pivot (shifted-data algorithm).  The LAST CTA of each channel
-// chunk to finish (ticket[blockIdx.x], zeroed ahead of the launch) combines the chunk's partials and writes stat + the
-// moving statistics -- statistics and finalize are one launch.
+// part: [nsplit][2][C] doubles (mean, M2) using a per-CTA pivot (shifted-data algorithm)
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float* __restrict__ x, int64_t rows, int C,
                                                               int64_t rows_per_split, int LC,
-                                                              double* __restrict__ part, unsigned* __restrict__ ticket,
-                                                              const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, float* __restrict__ mm,
-                                                              float* __restrict__ mv, float momentum, float eps,
-                                                              float* __restrict__ stat) {
+                                                              double* __restrict__ part) {
   nvae::pdl_enter();
   __shared__ float sm[kBnWarps][32][8];
   const int C4 = C >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -160,22 +114,56 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float* __res
       pq[i] = (double)qv[i] - (double)sv[i] * (double)sv[i] / n;
     }
   }
-  if (!last_block_of(ticket + blockIdx.x, gridDim.y)) return;
-  for (int j = warp; j < 4 * LC; j += kBnWarps) {  // one warp per channel of the chunk
-    const int c = blockIdx.x * 4 * LC + j;
-    if (c < C) bn_finalize_channel(part, (int)gridDim.y, rows, rows_per_split, C, c, gamma, beta, mm, mv, momentum, eps, stat);
-  }
 }
 
-// Inference: stat from the moving statistics (x is not read).
-__global__ void __launch_bounds__(256) bn_finalize_kernel(int C, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, const float* __restrict__ mm,
-                                                          const float* __restrict__ mv, float eps,
-                                                          float* __restrict__ stat) {
+// Combines the per-CTA (mean, M2) partials: one warp per channel, lane l takes splits l, l+32, ...; two passes of
+// plain sums (mean = sum n_s*m_s / n;  M2 = sum q_s + n_s*(m_s - mean)^2) and a fixed shuffle tree -- no serial
+// chain of divisions, deterministic.
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const double* __restrict__ part, int nsplit, int64_t rows,
+                                                          int64_t rows_per_split, int C,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ mm,
+                                                          float* __restrict__ mv, int training, float momentum,
+                                                          float eps, float* __restrict__ stat) {
   nvae::pdl_enter();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;
-  const float mean = mm[c], var = mv[c];
+  float mean, var;
+  if (training) {
+    const double n = (double)rows;
+    const double n_last = (double)(rows - (int64_t)(nsplit - 1) * rows_per_split), n_full = (double)rows_per_split;
+    // ONE pass over the partials (they are fp64, so the textbook sum n_s*m_s^2 - n*mu^2 has bits to spare; the shifted
+    // per-CTA pivots keep m_s small): three plain sums, one shuffle tree each -- half the dependent L2 round trips of
+    // the mean-then-M2 formulation
+    double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 4
+    for (int s = lane; s < nsplit; s += 32) {
+      const double ns = s == nsplit - 1 ? n_last : n_full;
+      const double m = part[((int64_t)s * 2) * C + c], q = part[((int64_t)s * 2 + 1) * C + c];
+      a0 += ns * m;
+      a1 += q;
+      a2 += ns * m * m;
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    const double mu = a0 / n;
+    double M2 = a1 + a2 - n * mu * mu;
+    if (M2 < 0) M2 = 0;
+    if (lane != 0) return;
+    mean = (float)mu;
+    var = (float)(M2 / n);
+    if (mm != nullptr) {
+      const double unbiased = n > 1 ? M2 / (n - 1) : M2 / n;
+      mm[c] = mm[c] * momentum + mean * (1.f - momentum);
+      mv[c] = mv[c] * momentum + (float)unbiased * (1.f - momentum);
+    }
+  } else {
+    if (lane != 0) return;
+    mean = mm[c];
+    var = mv[c];
+  }
   const float invstd = rsqrtf(var + eps);
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   const float scale = g * invstd;
@@ -240,16 +228,13 @@ __device__ __forceinline__ void g_and_xhat(const float4& dv, const float4& xv, c
                   dv.z * act_grad<ACT>(fmaf(xv.z, sc.z, sh.z)), dv.w * act_grad<ACT>(fmaf(xv.w, sc.w, sh.w)));
 }
 
-// part: [nsplit][2][C] doubles: sum g, sum g*xhat.  The last CTA of each channel chunk (ticket[blockIdx.x]) sums the chunk's
-// partials in split order -> dgamma, dbeta and bstat[2][C] = mean(g), mean(g*xhat): reduce and finalize are one launch.
+// part: [nsplit][2][C] doubles: sum g, sum g*xhat
 template <int ACT>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const float* __restrict__ dout,
                                                                    const float* __restrict__ x, int64_t rows, int C,
                                                                    int64_t rows_per_split, int LC,
                                                                    const float* __restrict__ stat, int up_h, int up_w,
-                                                                   double* __restrict__ part, unsigned* __restrict__ ticket,
-                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                   float* __restrict__ bstat) {
+                                                                   double* __restrict__ part) {
   nvae::pdl_enter();
   __shared__ float sm[kBnWarps][32][8];
   const int C4 = C >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -280,29 +265,31 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const float* 
     ps[0] = s.x; ps[1] = s.y; ps[2] = s.z; ps[3] = s.w;
     pq[0] = q.x; pq[1] = q.y; pq[2] = q.z; pq[3] = q.w;
   }
-  if (!last_block_of(ticket + blockIdx.x, gridDim.y)) return;
-  const int nsplit = (int)gridDim.y;
-  for (int j = warp; j < 4 * LC; j += kBnWarps) {  // one warp per channel of the chunk
-    const int c = blockIdx.x * 4 * LC + j;
-    if (c >= C) continue;
-    double sg = 0, sq = 0;
-#pragma unroll 4
-    for (int sp = lane; sp < nsplit; sp += 32) {
-      sg += __ldcg(part + ((int64_t)sp * 2) * C + c);
-      sq += __ldcg(part + ((int64_t)sp * 2 + 1) * C + c);
-    }
-    sg = warp_sum(sg);
-    sq = warp_sum(sq);
-    if (lane == 0) {
-      if (dgamma) dgamma[c] = (float)sq;
-      if (dbeta) dbeta[c] = (float)sg;
-      bstat[c] = (float)(sg / (double)rows);
-      bstat[C + c] = (float)(sq / (double)rows);
-    }
-  }
 }
 
-// bstat: [2][C] floats: mean(g), mean(g*xhat) (written by the last block of bn_bwd_reduce_kernel)
+// bstat: [2][C] floats: mean(g), mean(g*xhat)
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const double* __restrict__ part, int nsplit,
+                                                              int64_t rows, int C, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, float* __restrict__ bstat) {
+  nvae::pdl_enter();
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);  // one warp per channel
+  if (c >= C) return;
+  double sg = 0, sq = 0;
+#pragma unroll 4
+  for (int s = lane; s < nsplit; s += 32) {
+    sg += part[((int64_t)s * 2) * C + c];
+    sq += part[((int64_t)s * 2 + 1) * C + c];
+  }
+  sg = warp_sum(sg);
+  sq = warp_sum(sq);
+  if (lane != 0) return;
+  if (dgamma) dgamma[c] = (float)sq;
+  if (dbeta) dbeta[c] = (float)sg;
+  bstat[c] = (float)(sg / (double)rows);
+  bstat[C + c] = (float)(sq / (double)rows);
+}
+
 template <int ACT>
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ x, int64_t rows, int C4,
                                     const float* __restrict__ stat, const float* __restrict__ bstat, int up_h,
@@ -629,8 +616,7 @@ using namespace nvae;
 
 extern "C" size_t nvae_bn_ws_bytes(int64_t rows, int C) {
   (void)rows;
-  // [partials: nsplit x 2 x C doubles][bstat: 2C floats][tickets: one per channel chunk (<= C/4), zeroed per launch]
-  return (size_t)kBnMaxSplit * 2 * C * sizeof(double) + (size_t)2 * C * sizeof(float) + (size_t)C * sizeof(unsigned);
+  return (size_t)kBnMaxSplit * 2 * C * sizeof(double) + (size_t)2 * C * sizeof(float);
 }
 
 extern "C" int nvae_bn_stats(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
@@ -651,18 +637,13 @@ extern "C" int nvae_bn_stats(const float* x, int64_t rows, int C, const float* g
   }
   BnGeom g = bn_geom(rows, C);
   double* part = reinterpret_cast<double*>(ws);
-  if (training) {  // statistics + finalize (last block of each channel chunk) in one launch
-    const size_t pbytes = (size_t)g.nsplit * 2 * C * sizeof(double);
-    if (ws == nullptr || ws_bytes < pbytes + (size_t)g.nchunk * sizeof(unsigned)) return NVAE_E_WORKSPACE;
-    unsigned* ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + pbytes);
-    NVAE_CUDA_TRY(cudaMemsetAsync(ticket, 0, (size_t)g.nchunk * sizeof(unsigned), stream));
-    nvae::launch(bn_stats_kernel, dim3(g.nchunk, g.nsplit), kBnThreads, 0, stream, x, rows, C, g.rows_per_split, g.LC, part,
-                 ticket, gamma, beta, moving_mean, moving_var, momentum, eps, stat);
+  if (training) {
+    if (ws == nullptr || ws_bytes < (size_t)g.nsplit * 2 * C * sizeof(double)) return NVAE_E_WORKSPACE;
+    nvae::launch(bn_stats_kernel, dim3(g.nchunk, g.nsplit), kBnThreads, 0, stream, x, rows, C, g.rows_per_split, g.LC, part);
     NVAE_RETURN_IF_LAUNCH_FAILED();
-    return NVAE_OK;
   }
-  nvae::launch(bn_finalize_kernel, (C + 255) / 256, 256, 0, stream, C, gamma, beta, (const float*)moving_mean,
-               (const float*)moving_var, eps, stat);
+  nvae::launch(bn_finalize_kernel, (C + 7) / 8, 256, 0, stream, part, g.nsplit, rows, g.rows_per_split, C, gamma, beta,
+                                                           moving_mean, moving_var, training, momentum, eps, stat);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -745,17 +726,14 @@ static int bn_act_bwd_impl(const float* dout, const float* x, int64_t rows, int 
   float* bstat = nullptr;
   if (stat != nullptr && (training || dgamma != nullptr || dbeta != nullptr)) {
     BnGeom g = bn_geom(rows, C);
-    const size_t need = (size_t)g.nsplit * 2 * C * sizeof(double) + (size_t)2 * C * sizeof(float) +
-                        (size_t)g.nchunk * sizeof(unsigned);
+    const size_t need = (size_t)g.nsplit * 2 * C * sizeof(double) + (size_t)2 * C * sizeof(float);
     if (ws == nullptr || ws_bytes < need) return NVAE_E_WORKSPACE;
     double* part = reinterpret_cast<double*>(ws);
     float* bs = reinterpret_cast<float*>(part + (size_t)g.nsplit * 2 * C);
-    unsigned* ticket = reinterpret_cast<unsigned*>(bs + 2 * C);
-    NVAE_CUDA_TRY(cudaMemsetAsync(ticket, 0, (size_t)g.nchunk * sizeof(unsigned), stream));
-    // reduce + finalize (last block of each channel chunk: dgamma, dbeta, bstat) in one launch
     nvae::launch(bn_bwd_reduce_kernel<ACT>, dim3(g.nchunk, g.nsplit), kBnThreads, 0, stream, dout, x, rows, C, g.rows_per_split,
-                                                                                  g.LC, stat, up_h, up_w, part, ticket, dgamma,
-                                                                                  dbeta, bs);
+                                                                                  g.LC, stat, up_h, up_w, part);
+    NVAE_RETURN_IF_LAUNCH_FAILED();
+    nvae::launch(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, stream, part, g.nsplit, rows, C, dgamma, dbeta, bs);
     NVAE_RETURN_IF_LAUNCH_FAILED();
     if (training) bstat = bs;
   }

@@ -295,8 +295,7 @@ __global__ void __launch_bounds__(kDwThreads, 3) dwconv5x5_kernel(const float* _
 template <int WT>
 __global__ void __launch_bounds__(kDwThreads, 2) dwconv5x5_bwd_filter_kernel(
     const float* __restrict__ x, const float* __restrict__ stat, int act, const float* __restrict__ dy, int N, int H,
-    int W, int C, float* __restrict__ partial, int imgs, int PH, int PW, unsigned* __restrict__ ticket,
-    float* __restrict__ dw, float* __restrict__ dbias) {
+    int W, int C, float* __restrict__ partial, int imgs, int PH, int PW) {
   nvae::pdl_enter();
   extern __shared__ __align__(16) float smem[];
   float* tile = smem;                                  // haloed activated input
@@ -359,21 +358,23 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv5x5_bwd_filter_kernel(
     for (int wv = 0; wv < kDwThreads / 32; ++wv) s += red[(size_t)wv * 26 * kDwCC + i];
     partial[((int64_t)blockIdx.y * 26 + i / kDwCC) * C + c0 + (i % kDwCC)] = s;
   }
-  // the last image group of this channel chunk to finish adds the chunk's partials in group order (deterministic)
-  if (!last_block_of(ticket + blockIdx.x, gridDim.y)) return;
-  const int ngroups = (int)gridDim.y;
-  for (int i = threadIdx.x; i < 26 * kDwCC; i += kDwThreads) {
-    const int64_t e = (int64_t)(i / kDwCC) * C + c0 + (i % kDwCC);
+}
+
+__global__ void dwconv5x5_bwd_filter_reduce_kernel(const float* __restrict__ partial, int ngroups, int C,
+                                                   float* __restrict__ dw, float* __restrict__ dbias) {
+  nvae::pdl_enter();
+  const int total = 26 * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int g = 0;
     for (; g + 3 < ngroups; g += 4) {  // four loads in flight; fixed association
-      s0 += __ldcg(partial + (int64_t)g * 26 * C + e); s1 += __ldcg(partial + (int64_t)(g + 1) * 26 * C + e);
-      s2 += __ldcg(partial + (int64_t)(g + 2) * 26 * C + e); s3 += __ldcg(partial + (int64_t)(g + 3) * 26 * C + e);
+      s0 += partial[(int64_t)g * total + i]; s1 += partial[(int64_t)(g + 1) * total + i];
+      s2 += partial[(int64_t)(g + 2) * total + i]; s3 += partial[(int64_t)(g + 3) * total + i];
     }
-    for (; g < ngroups; ++g) s0 += __ldcg(partial + (int64_t)g * 26 * C + e);
+    for (; g < ngroups; ++g) s0 += partial[(int64_t)g * total + i];
     const float s = (s0 + s1) + (s2 + s3);
-    if (i < 25 * kDwCC) dw[e] = s;
-    else if (dbias != nullptr) dbias[c0 + (i % kDwCC)] = s;
+    if (i < 25 * C) dw[i] = s;
+    else if (dbias != nullptr) dbias[i - 25 * C] = s;
   }
 }
 
@@ -441,7 +442,7 @@ extern "C" int nvae_dwconv5x5_bwd_data(const float* dy, int N, int H, int W, int
 extern "C" size_t nvae_dwconv5x5_bwd_filter_ws_bytes(int N, int H, int W, int C) {
   if (dw_check(N, H, W, C)) return 0;
   DwGeom g = dw_geom(N, H, W, C);
-  return (size_t)g.ngroups * 26 * C * sizeof(float) + (size_t)g.nchunks * sizeof(unsigned);
+  return (size_t)g.ngroups * 26 * C * sizeof(float);
 }
 
 extern "C" int nvae_dwconv5x5_bwd_filter(const float* x, const float* stat, int act, const float* dy, int N, int H,
@@ -451,14 +452,11 @@ extern "C" int nvae_dwconv5x5_bwd_filter(const float* x, const float* stat, int 
   if (rc) return rc;
   if (!x || !dy || !dw) return NVAE_E_NULLPTR;
   DwGeom g = dw_geom(N, H, W, C);
-  if (ws == nullptr || ws_bytes < (size_t)g.ngroups * 26 * C * sizeof(float) + (size_t)g.nchunks * sizeof(unsigned))
-    return NVAE_E_WORKSPACE;
+  if (ws == nullptr || ws_bytes < (size_t)g.ngroups * 26 * C * sizeof(float)) return NVAE_E_WORKSPACE;
   size_t dfloats = (size_t)g.imgs * H * W * kDwCC;
   if (dfloats < (size_t)(kDwThreads / 32) * 26 * kDwCC) dfloats = (size_t)(kDwThreads / 32) * 26 * kDwCC;  // cross-warp buffer
   const size_t smem = (g.smem_tile + dfloats) * sizeof(float);
   float* partial = reinterpret_cast<float*>(ws);
-  unsigned* ticket = reinterpret_cast<unsigned*>(partial + (size_t)g.ngroups * 26 * C);
-  NVAE_CUDA_TRY(cudaMemsetAsync(ticket, 0, (size_t)g.nchunks * sizeof(unsigned), stream));
   const dim3 grid(g.nchunks, g.ngroups);
 #define NVAE_DW_FILTER(WT_)                                                                                           \
   do {                                                                                                                \
@@ -469,13 +467,15 @@ extern "C" int nvae_dwconv5x5_bwd_filter(const float* x, const float* stat, int 
       configured = true;                                                                                              \
     }                                                                                                                 \
     nvae::launch(dwconv5x5_bwd_filter_kernel<WT_>, grid, kDwThreads, smem, stream, x, stat, act, dy, N, H, W, C, partial, g.imgs, \
-                                                                         g.PH, g.PW, ticket, dw, dbias);              \
+                                                                         g.PH, g.PW);                                 \
   } while (0)
   if (W <= 4) NVAE_DW_FILTER(4);
   else if (W <= 8) NVAE_DW_FILTER(8);
   else if (W <= 16) NVAE_DW_FILTER(16);
   else return NVAE_E_UNSUPPORTED;
 #undef NVAE_DW_FILTER
+  NVAE_RETURN_IF_LAUNCH_FAILED();
+  nvae::launch(dwconv5x5_bwd_filter_reduce_kernel, (26 * C + 255) / 256, 256, 0, stream, partial, g.ngroups, C, dw, dbias);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }

@@ -1,6 +1,6 @@
 // Squeeze-and-Excitation gate + residual merge (common.py:129-142 fused with encoder.py:107,
 // decoder.py:147, preprocess.py:107, postprocess.py:58).  Bandwidth-bound: one pass over t for the
-// global pool (+ the two tiny dense layers), one pass (cache hits) for the gated residual -- one cluster launch.
+// global pool (+ the two tiny dense layers in the same CTA), one pass for the gated residual.
 #include "common.cuh"
 
 namespace nvae {
@@ -8,47 +8,33 @@ namespace nvae {
 constexpr int kSeThreads = 256;
 constexpr int kSeMaxC = 1024;
 constexpr int kSeMaxHid = 64;
+constexpr size_t kSeFuseBytes = 64 * 1024;  // per-sample tensor size up to which the per-sample CTA also applies the gate
 
-// ---- cluster versions: S CTAs per sample -------------------------------------------------------------------------
-// One CTA per sample leaves the machine almost empty (144 CTAs of 256 threads on 148 SMs, each walking its sample with
-// four loads in flight: 15-29 % of the HBM rate on tensors beyond L2).  Here a sample is owned by a thread-block CLUSTER
-// of S <= 8 CTAs that split its rows: each CTA pools its rows, the per-channel partial sums are exchanged through
-// distributed shared memory and added in rank order (fixed association: every CTA of the cluster gets the same bits),
-// every CTA then computes the (tiny) dense -> relu -> dense -> sigmoid chain redundantly and applies the gate to its own
-// rows, which it streamed a moment ago (L1/L2 hits).  Forward and backward are ONE launch each at any tensor size.
-__device__ __forceinline__ int se_cluster_rows(int HW, int S, int rank, int* r0) {
-  const int rps = (HW + S - 1) / S;
-  *r0 = rank * rps;
-  const int r1 = *r0 + rps < HW ? *r0 + rps : HW;
-  return r1 > *r0 ? r1 : *r0;
-}
-
-__global__ void __launch_bounds__(kSeThreads) se_fwd_cluster_kernel(
+// One CTA per sample: pooled' = affine(mean_hw t), hidden = relu(W1^T pooled' + b1),
+// gate = sigmoid(W2^T hidden + b2).
+__global__ void __launch_bounds__(kSeThreads) se_pool_gate_kernel(
     const float* __restrict__ t, const float* __restrict__ stat, int HW, int C, int hid, const float* __restrict__ w1,
     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
     float* __restrict__ pooled, float* __restrict__ hidden, float* __restrict__ gate, const float* __restrict__ xres,
-    float alpha, float beta, float* __restrict__ y, int S) {
+    float alpha, float beta, float* __restrict__ y) {
   nvae::pdl_enter();
   __shared__ float part[kSeThreads * 4];
-  __shared__ __align__(16) float cpart[kSeMaxC];  // this CTA's per-channel partial sums (read by the cluster)
   __shared__ __align__(16) float spool[kSeMaxC];
   __shared__ float shid[kSeMaxHid];
-  const int b = blockIdx.x / S, rank = blockIdx.x % S, C4 = C >> 2, tid = threadIdx.x;
-  const int G = kSeThreads / C4, grp = tid / C4, c4 = tid % C4;
-  int r0;
-  const int r1 = se_cluster_rows(HW, S, rank, &r0);
+  const int b = blockIdx.x, C4 = C >> 2, tid = threadIdx.x;
+  const int G = kSeThreads / C4;  // row groups
+  const int grp = tid / C4, c4 = tid % C4;
   const float* tb = t + (int64_t)b * HW * C;
   float4 acc = make_float4(0, 0, 0, 0);
   if (grp < G) {
-    int r = r0 + grp;
-    for (; r + 7 * G < r1; r += 8 * G) {  // eight 128-bit loads in flight per thread
-      float4 v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = ldg4(tb + (int64_t)(r + j * G) * C + c4 * 4);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+    int r = grp;
+    for (; r + 3 * G < HW; r += 4 * G) {
+      const float4 v0 = ldg4(tb + (int64_t)r * C + c4 * 4), v1 = ldg4(tb + (int64_t)(r + G) * C + c4 * 4),
+                   v2 = ldg4(tb + (int64_t)(r + 2 * G) * C + c4 * 4), v3 = ldg4(tb + (int64_t)(r + 3 * G) * C + c4 * 4);
+      acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+      acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
     }
-    for (; r < r1; r += G) {
+    for (; r < HW; r += G) {
       const float4 v = ldg4(tb + (int64_t)r * C + c4 * 4);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
@@ -58,18 +44,12 @@ __global__ void __launch_bounds__(kSeThreads) se_fwd_cluster_kernel(
   for (int c = tid; c < C; c += kSeThreads) {
     float s = 0.f;
     for (int g = 0; g < G; ++g) s += part[(g * C4 + (c >> 2)) * 4 + (c & 3)];
-    cpart[c] = s;
-  }
-  cluster_barrier();
-  for (int c = tid; c < C; c += kSeThreads) {
-    float s = 0.f;
-    for (int j = 0; j < S; ++j) s += dsmem_ld_f32(&cpart[c], j);
     s *= 1.f / (float)HW;
     if (stat != nullptr) s = fmaf(s, stat[2 * C + c], stat[3 * C + c]);
     spool[c] = s;
-    if (rank == 0) pooled[(int64_t)b * C + c] = s;
+    pooled[(int64_t)b * C + c] = s;
   }
-  cluster_barrier();  // every CTA is done reading its peers' partials: from here on CTAs are independent
+  __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
   for (int j = warp; j < hid; j += kSeThreads / 32) {
     float s = 0.f;
@@ -78,7 +58,7 @@ __global__ void __launch_bounds__(kSeThreads) se_fwd_cluster_kernel(
     if (lane == 0) {
       s = fmaxf(s + b1[j], 0.f);
       shid[j] = s;
-      if (rank == 0) hidden[(int64_t)b * hid + j] = s;
+      hidden[(int64_t)b * hid + j] = s;
     }
   }
   __syncthreads();
@@ -86,61 +66,69 @@ __global__ void __launch_bounds__(kSeThreads) se_fwd_cluster_kernel(
     float s = b2[c];
     for (int j = 0; j < hid; ++j) s = fmaf(shid[j], __ldg(w2 + (int64_t)j * C + c), s);
     s = 1.f / (1.f + expf(-s));
-    if (rank == 0) gate[(int64_t)b * C + c] = s;
+    gate[(int64_t)b * C + c] = s;
     spool[c] = s;  // (the pooled values are no longer needed)
   }
+  if (y == nullptr) return;
+  // fused residual merge for small samples: y = alpha*xres + beta*t'*gate -- the sample's t was just streamed by this
+  // CTA (L1/L2 hits), and one launch disappears
   __syncthreads();
-  // gated residual merge of this CTA's rows: y = alpha*xres + beta*t'*gate
-  if (grp >= G) return;
-  float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0);
-  if (stat != nullptr) {
-    sc = ldg4(stat + 2 * C + c4 * 4);
-    sh = ldg4(stat + 3 * C + c4 * 4);
-  }
-  const float4 g = *reinterpret_cast<const float4*>(&spool[c4 * 4]);
-  const float bx = beta * g.x, by = beta * g.y, bz = beta * g.z, bw = beta * g.w;
   const float* xb = xres + (int64_t)b * HW * C;
   float* yb = y + (int64_t)b * HW * C;
-  for (int rb = r0 + grp; rb < r1; rb += 4 * G) {
-    float4 v[4], xr[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = rb + j * G;
-      if (r < r1) {
-        v[j] = ldg4(tb + (int64_t)r * C + c4 * 4);
-        xr[j] = ldg4(xb + (int64_t)r * C + c4 * 4);
-      }
+  const int n4 = HW * C4;
+  for (int i = tid; i < n4; i += kSeThreads) {
+    const int k4 = i % C4;
+    float4 v = ldg4(tb + (int64_t)i * 4);
+    if (stat != nullptr) {
+      const float4 sc = ldg4(stat + 2 * C + k4 * 4), sh = ldg4(stat + 3 * C + k4 * 4);
+      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = rb + j * G;
-      if (r >= r1) break;
-      float4 o;
-      o.x = fmaf(alpha, xr[j].x, bx * fmaf(v[j].x, sc.x, sh.x)); o.y = fmaf(alpha, xr[j].y, by * fmaf(v[j].y, sc.y, sh.y));
-      o.z = fmaf(alpha, xr[j].z, bz * fmaf(v[j].z, sc.z, sh.z)); o.w = fmaf(alpha, xr[j].w, bw * fmaf(v[j].w, sc.w, sh.w));
-      stg4(yb + (int64_t)r * C + c4 * 4, o);
-    }
+    const float4 g = *reinterpret_cast<const float4*>(&spool[k4 * 4]);
+    const float4 xr = ldg4(xb + (int64_t)i * 4);
+    float4 o;
+    o.x = fmaf(alpha, xr.x, beta * v.x * g.x); o.y = fmaf(alpha, xr.y, beta * v.y * g.y);
+    o.z = fmaf(alpha, xr.z, beta * v.z * g.z); o.w = fmaf(alpha, xr.w, beta * v.w * g.w);
+    stg4(yb + (int64_t)i * 4, o);
   }
 }
 
-// Backward: r[c] = beta*sum_hw dy*t' (cluster reduction), chain through sigmoid / dense2 / relu / dense1 in every CTA,
-// rank 0 writes dz2 [B,C], dh [B,hid], dpool [B,C] for the dense-layer gradients; then on this CTA's rows
-// dt' = beta*dy*gate + dpool/HW and dxres (+)= alpha*dy.
-__global__ void __launch_bounds__(kSeThreads) se_bwd_cluster_kernel(
+// y = alpha*xres + beta*t'*gate[b,c]
+__global__ void se_apply_kernel(const float* __restrict__ t, const float* __restrict__ stat,
+                                const float* __restrict__ xres, const float* __restrict__ gate, int64_t n4, int C4,
+                                int64_t hwc4, float alpha, float beta, float* __restrict__ y) {
+  nvae::pdl_enter();
+  const int C = C4 * 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    const int64_t b = i / hwc4;
+    float4 v = ldg4(t + i * 4);
+    if (stat != nullptr) {
+      const float4 sc = ldg4(stat + 2 * C + c4 * 4), sh = ldg4(stat + 3 * C + c4 * 4);
+      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    }
+    const float4 g = ldg4(gate + b * C + c4 * 4);
+    const float4 xr = ldg4(xres + i * 4);
+    float4 o;
+    o.x = fmaf(alpha, xr.x, beta * v.x * g.x); o.y = fmaf(alpha, xr.y, beta * v.y * g.y);
+    o.z = fmaf(alpha, xr.z, beta * v.z * g.z); o.w = fmaf(alpha, xr.w, beta * v.w * g.w);
+    stg4(y + i * 4, o);
+  }
+}
+
+// One CTA per sample: r[c] = beta*sum_hw dy*t'; chain through sigmoid / dense2 / relu / dense1.
+// Writes dz2 [B,C], dh [B,hid], dpool [B,C].
+__global__ void __launch_bounds__(kSeThreads) se_bwd_gate_kernel(
     const float* __restrict__ dy, const float* __restrict__ t, const float* __restrict__ stat, int HW, int C, int hid,
     const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ hidden,
     const float* __restrict__ gate, float beta, float* __restrict__ dz2, float* __restrict__ dh,
-    float* __restrict__ dpool, float alpha, float* __restrict__ dt, float* __restrict__ dxres, int dxres_accumulate,
-    int S) {
+    float* __restrict__ dpool, float alpha, float* __restrict__ dt, float* __restrict__ dxres, int dxres_accumulate) {
   nvae::pdl_enter();
   __shared__ float part[kSeThreads * 4];
-  __shared__ __align__(16) float cpart[kSeMaxC];
   __shared__ __align__(16) float sdz[kSeMaxC];
   __shared__ float sdh[kSeMaxHid];
-  const int b = blockIdx.x / S, rank = blockIdx.x % S, C4 = C >> 2, tid = threadIdx.x;
-  const int G = kSeThreads / C4, grp = tid / C4, c4 = tid % C4;
-  int r0;
-  const int r1 = se_cluster_rows(HW, S, rank, &r0);
+  const int b = blockIdx.x, C4 = C >> 2, tid = threadIdx.x;
+  const int G = kSeThreads / C4;
+  const int grp = tid / C4, c4 = tid % C4;
   const float* tb = t + (int64_t)b * HW * C;
   const float* db = dy + (int64_t)b * HW * C;
   float4 acc = make_float4(0, 0, 0, 0);
@@ -150,21 +138,8 @@ __global__ void __launch_bounds__(kSeThreads) se_bwd_cluster_kernel(
       sc = ldg4(stat + 2 * C + c4 * 4);
       sh = ldg4(stat + 3 * C + c4 * 4);
     }
-    int r = r0 + grp;
-    for (; r + 3 * G < r1; r += 4 * G) {  // eight 128-bit loads in flight per thread
-      float4 v[4], d[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[j] = ldg4(tb + (int64_t)(r + j * G) * C + c4 * 4);
-        d[j] = ldg4(db + (int64_t)(r + j * G) * C + c4 * 4);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc.x = fmaf(d[j].x, fmaf(v[j].x, sc.x, sh.x), acc.x); acc.y = fmaf(d[j].y, fmaf(v[j].y, sc.y, sh.y), acc.y);
-        acc.z = fmaf(d[j].z, fmaf(v[j].z, sc.z, sh.z), acc.z); acc.w = fmaf(d[j].w, fmaf(v[j].w, sc.w, sh.w), acc.w);
-      }
-    }
-    for (; r < r1; r += G) {
+#pragma unroll 4
+    for (int r = grp; r < HW; r += G) {
       const float4 v = ldg4(tb + (int64_t)r * C + c4 * 4), d = ldg4(db + (int64_t)r * C + c4 * 4);
       acc.x = fmaf(d.x, fmaf(v.x, sc.x, sh.x), acc.x); acc.y = fmaf(d.y, fmaf(v.y, sc.y, sh.y), acc.y);
       acc.z = fmaf(d.z, fmaf(v.z, sc.z, sh.z), acc.z); acc.w = fmaf(d.w, fmaf(v.w, sc.w, sh.w), acc.w);
@@ -175,18 +150,12 @@ __global__ void __launch_bounds__(kSeThreads) se_bwd_cluster_kernel(
   for (int c = tid; c < C; c += kSeThreads) {
     float s = 0.f;
     for (int g = 0; g < G; ++g) s += part[(g * C4 + (c >> 2)) * 4 + (c & 3)];
-    cpart[c] = s;
-  }
-  cluster_barrier();
-  for (int c = tid; c < C; c += kSeThreads) {
-    float s = 0.f;
-    for (int j = 0; j < S; ++j) s += dsmem_ld_f32(&cpart[c], j);
     const float gt = gate[(int64_t)b * C + c];
     const float d = beta * s * gt * (1.f - gt);
     sdz[c] = d;
-    if (rank == 0) dz2[(int64_t)b * C + c] = d;
+    dz2[(int64_t)b * C + c] = d;
   }
-  cluster_barrier();  // peers are done with this CTA's partials
+  __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
   for (int j = warp; j < hid; j += kSeThreads / 32) {
     float s = 0.f;
@@ -195,47 +164,40 @@ __global__ void __launch_bounds__(kSeThreads) se_bwd_cluster_kernel(
     if (lane == 0) {
       s = hidden[(int64_t)b * hid + j] > 0.f ? s : 0.f;
       sdh[j] = s;
-      if (rank == 0) dh[(int64_t)b * hid + j] = s;
+      dh[(int64_t)b * hid + j] = s;
     }
   }
   __syncthreads();
+  __syncthreads();  // (sdz is reused below: everyone is done reading it)
   for (int c = tid; c < C; c += kSeThreads) {
     float s = 0.f;
     for (int j = 0; j < hid; ++j) s = fmaf(sdh[j], __ldg(w1 + (int64_t)c * hid + j), s);
-    if (rank == 0) dpool[(int64_t)b * C + c] = s;
-    sdz[c] = s;  // (every thread rewrites only the entries it read above... after the barrier below all are dpool)
+    dpool[(int64_t)b * C + c] = s;
+    sdz[c] = s;
   }
+  if (dt == nullptr) return;
+  // fused apply for small samples: dt' = beta*dy*gate + dpool/HW ; dxres (+)= alpha*dy
   __syncthreads();
-  if (grp >= G) return;
   const float inv_hw = 1.f / (float)HW;
-  const float4 g = ldg4(gate + (int64_t)b * C + c4 * 4);
-  const float4 p = *reinterpret_cast<const float4*>(&sdz[c4 * 4]);
-  const float gx = beta * g.x, gy = beta * g.y, gz = beta * g.z, gw = beta * g.w;
-  const float px = p.x * inv_hw, py = p.y * inv_hw, pz = p.z * inv_hw, pw = p.w * inv_hw;
+  const float* gb = gate + (int64_t)b * C;
   float* dtb = dt + (int64_t)b * HW * C;
   float* dxb = dxres != nullptr ? dxres + (int64_t)b * HW * C : nullptr;
-  for (int rb = r0 + grp; rb < r1; rb += 4 * G) {
-    float4 d[4], e[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = rb + j * G;
-      if (r < r1) {
-        d[j] = ldg4(db + (int64_t)r * C + c4 * 4);
-        if (dxb != nullptr && dxres_accumulate) e[j] = *reinterpret_cast<const float4*>(dxb + (int64_t)r * C + c4 * 4);
+  const int n4 = HW * C4;
+  for (int i = tid; i < n4; i += kSeThreads) {
+    const int k4 = i % C4;
+    const float4 d = ldg4(db + (int64_t)i * 4), g = ldg4(gb + k4 * 4);
+    const float4 p = *reinterpret_cast<const float4*>(&sdz[k4 * 4]);
+    float4 o;
+    o.x = fmaf(beta * d.x, g.x, p.x * inv_hw); o.y = fmaf(beta * d.y, g.y, p.y * inv_hw);
+    o.z = fmaf(beta * d.z, g.z, p.z * inv_hw); o.w = fmaf(beta * d.w, g.w, p.w * inv_hw);
+    stg4(dtb + (int64_t)i * 4, o);
+    if (dxb != nullptr) {
+      float4 r = make_float4(alpha * d.x, alpha * d.y, alpha * d.z, alpha * d.w);
+      if (dxres_accumulate) {
+        const float4 e = *reinterpret_cast<const float4*>(dxb + (int64_t)i * 4);
+        r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
       }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = rb + j * G;
-      if (r >= r1) break;
-      float4 o;
-      o.x = fmaf(d[j].x, gx, px); o.y = fmaf(d[j].y, gy, py); o.z = fmaf(d[j].z, gz, pz); o.w = fmaf(d[j].w, gw, pw);
-      stg4(dtb + (int64_t)r * C + c4 * 4, o);
-      if (dxb != nullptr) {
-        float4 q = make_float4(alpha * d[j].x, alpha * d[j].y, alpha * d[j].z, alpha * d[j].w);
-        if (dxres_accumulate) { q.x += e[j].x; q.y += e[j].y; q.z += e[j].z; q.w += e[j].w; }
-        stg4(dxb + (int64_t)r * C + c4 * 4, q);
-      }
+      stg4(dxb + (int64_t)i * 4, r);
     }
   }
 }
@@ -301,18 +263,41 @@ __global__ void se_bwd_weights_kernel(const float* __restrict__ pooled, const fl
   if (valid && sub == 0) *out = r;
 }
 
+// dt' = beta*dy*gate + dpool/HW ; dxres (+)= alpha*dy
+__global__ void se_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ gate,
+                                    const float* __restrict__ dpool, int64_t n4, int C4, int64_t hwc4, float inv_hw,
+                                    float alpha, float beta, float* __restrict__ dt, float* __restrict__ dxres,
+                                    int dxres_accumulate) {
+  nvae::pdl_enter();
+  const int C = C4 * 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    const int64_t b = i / hwc4;
+    const float4 d = ldg4(dy + i * 4), g = ldg4(gate + b * C + c4 * 4), p = ldg4(dpool + b * C + c4 * 4);
+    float4 o;
+    o.x = fmaf(beta * d.x, g.x, p.x * inv_hw); o.y = fmaf(beta * d.y, g.y, p.y * inv_hw);
+    o.z = fmaf(beta * d.z, g.z, p.z * inv_hw); o.w = fmaf(beta * d.w, g.w, p.w * inv_hw);
+    stg4(dt + i * 4, o);
+    if (dxres != nullptr) {
+      float4 r = make_float4(alpha * d.x, alpha * d.y, alpha * d.z, alpha * d.w);
+      if (dxres_accumulate) {
+        const float4 e = *reinterpret_cast<const float4*>(dxres + i * 4);
+        r.x += e.x; r.y += e.y; r.z += e.z; r.w += e.w;
+      }
+      stg4(dxres + i * 4, r);
+    }
+  }
+}
+
+static int se_grid(int64_t n, int threads) {
+  int64_t b = ceil_div(n, threads);
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
 }  // namespace nvae
 
 using namespace nvae;
-
-// CTAs per sample: a power of two <= 8 (portable cluster size) with at least one pass of rows per CTA, doubled until the
-// grid holds ~4 CTAs per SM
-static int se_cluster_size(int B, int HW, int C) {
-  const int G = kSeThreads / (C / 4);
-  int S = 1;
-  while (S < 8 && (int64_t)B * S < 4 * kNumSMs && 2 * S * G <= HW) S *= 2;
-  return S;
-}
 
 static int se_check(int B, int HW, int C, int hid) {
   if (B <= 0 || HW <= 0 || C <= 0 || (C & 3) || C > kSeMaxC || hid <= 0 || hid > kSeMaxHid) return NVAE_E_BADSHAPE;
@@ -326,9 +311,16 @@ extern "C" int nvae_se_fwd(const float* t, const float* stat, const float* xres,
   int rc = se_check(B, HW, C, hid);
   if (rc) return rc;
   if (!t || !xres || !w1 || !b1 || !w2 || !b2 || !pooled || !hidden || !gate || !y) return NVAE_E_NULLPTR;
-  const int S = se_cluster_size(B, HW, C);
-  launch_cluster(se_fwd_cluster_kernel, dim3(B * S), kSeThreads, 0, stream, dim3(S, 1, 1), t, stat, HW, C, hid, w1, b1, w2, b2,
-                 pooled, hidden, gate, xres, alpha, beta, y, S);
+  // one CTA per sample also merges the residual when a sample is small (<= 64 KB): at the model's 4x4 / 8x8 / 16x16
+  // scales that is one launch instead of two and the second read of t never leaves the SM's cache
+  const bool fuse = (size_t)HW * C * sizeof(float) <= kSeFuseBytes;
+  nvae::launch(se_pool_gate_kernel, B, kSeThreads, 0, stream, t, stat, HW, C, hid, w1, b1, w2, b2, pooled, hidden, gate, xres,
+               alpha, beta, fuse ? y : (float*)nullptr);
+  NVAE_RETURN_IF_LAUNCH_FAILED();
+  if (fuse) return NVAE_OK;
+  const int64_t n4 = (int64_t)B * HW * (C / 4);
+  nvae::launch(se_apply_kernel, se_grid(n4, 256), 256, 0, stream, t, stat, xres, gate, n4, C / 4, (int64_t)HW * (C / 4), alpha,
+                                                        beta, y);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
@@ -348,12 +340,17 @@ extern "C" int nvae_se_bwd(const float* dy, const float* t, const float* stat, i
   float* dz2 = reinterpret_cast<float*>(ws);
   float* dpool = dz2 + (size_t)B * C;
   float* dh = dpool + (size_t)B * C;
-  const int S = se_cluster_size(B, HW, C);
-  launch_cluster(se_bwd_cluster_kernel, dim3(B * S), kSeThreads, 0, stream, dim3(S, 1, 1), dy, t, stat, HW, C, hid, w1, w2,
-                 hidden, gate, beta, dz2, dh, dpool, alpha, dt, dxres, dxres_accumulate, S);
+  const bool fuse = (size_t)HW * C * sizeof(float) <= kSeFuseBytes;
+  nvae::launch(se_bwd_gate_kernel, B, kSeThreads, 0, stream, dy, t, stat, HW, C, hid, w1, w2, hidden, gate, beta, dz2, dh, dpool,
+               alpha, fuse ? dt : (float*)nullptr, dxres, dxres_accumulate);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   const int total = 2 * C * hid + C + hid;
   nvae::launch(se_bwd_weights_kernel, (total * 8 + 127) / 128, 128, 0, stream, pooled, hidden, dz2, dh, B, C, hid, dw1, db1, dw2, db2);
+  NVAE_RETURN_IF_LAUNCH_FAILED();
+  if (fuse) return NVAE_OK;
+  const int64_t n4 = (int64_t)B * HW * (C / 4);
+  nvae::launch(se_bwd_apply_kernel, se_grid(n4, 256), 256, 0, stream, dy, gate, dpool, n4, C / 4, (int64_t)HW * (C / 4),
+                                                            1.f / (float)HW, alpha, beta, dt, dxres, dxres_accumulate);
   NVAE_RETURN_IF_LAUNCH_FAILED();
   return NVAE_OK;
 }
