@@ -2,8 +2,6 @@
 // each CTA stages a zero-haloed [imgs][H+4][W+4..][32ch] tile in shared memory (128-byte channel
 // rows -> fully coalesced 128-bit global loads, conflict-free LDS.128), with the BatchNorm-apply +
 // swish of decoder.py:141 fused into the staging so the activated tensor never exists in HBM.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace nvae {
@@ -380,171 +378,6 @@ __global__ void dwconv5x5_bwd_filter_reduce_kernel(const float* __restrict__ par
   }
 }
 
-// ---- sliding-window kernels (the shapes the model and the micro-benchmarks use) -----------------------------------
-// ncu on the staged kernels above ([256,14,14,384]): 22 % of the HBM rate, NOT bandwidth-bound -- 0.66 barrier stalls per
-// issued instruction, 25 % occupancy (92 KB of shared memory per CTA), LDS-bound inner loop.  These kernels use no shared
-// memory and no barrier at all: a thread owns ONE channel (a warp = 32 adjacent channels, so every global access is a
-// fully coalesced 128-byte row segment) of one (image, SW-column strip) and slides down the rows with the 25 taps, five
-// rows of accumulators and the current input row in REGISTERS.  Each input element is loaded once per strip (straight from
-// global memory / L2; the BatchNorm-apply + swish runs on it in registers) and used for up to 25 FMAs: 0.06 - 0.1 loads per
-// FMA instead of 0.24 shared-memory loads, and nothing to synchronise.  H and the strip width are compile-time, the row
-// loop is fully unrolled, so every register-array index is static.
-template <int H, int SW, bool FLIP>
-__global__ void __launch_bounds__(256, 2) dw_slide_kernel(const float* __restrict__ x, const float* __restrict__ stat, int act,
-                                                       int N, int W, int C, const float* __restrict__ wts,
-                                                       const float* __restrict__ bias, float* __restrict__ y, int nstrips,
-                                                       int ipw) {
-  nvae::pdl_enter();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * kDwCC + lane;
-  float wreg[25];
-#pragma unroll
-  for (int t = 0; t < 25; ++t) wreg[t] = __ldg(wts + (int64_t)(FLIP ? 24 - t : t) * C + c);
-  const float bv = (!FLIP && bias != nullptr) ? __ldg(bias + c) : 0.f;
-  const bool prologue = !FLIP && stat != nullptr;
-  const float sc = prologue ? __ldg(stat + 2 * C + c) : 1.f, sh = prologue ? __ldg(stat + 3 * C + c) : 0.f;
-  const bool activate = prologue || (!FLIP && act != NVAE_ACT_NONE);
-  const int nitems = N * nstrips;
-  int it = (blockIdx.y * (kDwThreads / 32) + warp) * ipw;
-  for (int k = 0; k < ipw && it < nitems; ++k, ++it) {
-    const int img = it / nstrips, w0 = (it - img * nstrips) * SW;
-    const float* xb = x + (int64_t)img * H * W * C + c;
-    float* yb = y + (int64_t)img * H * W * C + c;
-    float acc[5][SW];
-#pragma unroll
-    for (int q = 0; q < 5; ++q)
-#pragma unroll
-      for (int j = 0; j < SW; ++j) acc[q][j] = bv;
-#pragma unroll
-    for (int r = 0; r < H; ++r) {
-      float xr[SW + 4];
-#pragma unroll
-      for (int j = 0; j < SW + 4; ++j) {
-        const int wc = w0 - 2 + j;
-        float v = 0.f;
-        if (wc >= 0 && wc < W) {
-          v = __ldg(xb + (int64_t)(r * W + wc) * C);
-          if (activate) v = act_fwd_rt(fmaf(v, sc, sh), act);
-        }
-        xr[j] = v;
-      }
-#pragma unroll
-      for (int tr = 0; tr < 5; ++tr) {
-        const int h = r + 2 - tr;  // output row fed by input row r through tap row tr
-        if (h < 0 || h >= H) continue;
-#pragma unroll
-        for (int sx = 0; sx < 5; ++sx)
-#pragma unroll
-          for (int j = 0; j < SW; ++j) acc[h % 5][j] = fmaf(xr[j + sx], wreg[tr * 5 + sx], acc[h % 5][j]);
-      }
-      if (r >= 2) {  // output row r - 2 has seen its last input row
-#pragma unroll
-        for (int j = 0; j < SW; ++j) {
-          if (w0 + j < W) yb[(int64_t)((r - 2) * W + w0 + j) * C] = acc[(r - 2) % 5][j];
-          acc[(r - 2) % 5][j] = bv;
-        }
-      }
-    }
-#pragma unroll
-    for (int h = (H >= 2 ? H - 2 : 0); h < H; ++h)
-#pragma unroll
-      for (int j = 0; j < SW; ++j)
-        if (w0 + j < W) yb[(int64_t)(h * W + w0 + j) * C] = acc[h % 5][j];
-  }
-}
-
-// Backward-filter, same mapping: a thread keeps the 25 tap sums + the bias sum of its channel in registers across ALL the
-// (image, strip) items its warp walks, with five dy rows and the current (activated) input row in registers; the 8 warps of
-// a CTA are combined through shared memory in warp order and written as one partial per CTA (summed by the reduce kernel).
-template <int H, int SW>
-__global__ void __launch_bounds__(256, 2) dw_slide_filter_kernel(const float* __restrict__ x, const float* __restrict__ stat,
-                                                              int act, const float* __restrict__ dy, int N, int W, int C,
-                                                              float* __restrict__ partial, int nstrips, int items_per_cta) {
-  nvae::pdl_enter();
-  __shared__ float red[kDwThreads / 32][26][kDwCC];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * kDwCC + lane;
-  const bool prologue = stat != nullptr;
-  const float sc = prologue ? __ldg(stat + 2 * C + c) : 1.f, sh = prologue ? __ldg(stat + 3 * C + c) : 0.f;
-  const bool activate = prologue || act != NVAE_ACT_NONE;
-  float acc[26];
-#pragma unroll
-  for (int i = 0; i < 26; ++i) acc[i] = 0.f;
-  const int nitems = N * nstrips;
-  const int it0 = blockIdx.y * items_per_cta;
-  const int it1 = it0 + items_per_cta < nitems ? it0 + items_per_cta : nitems;
-  for (int it = it0 + warp; it < it1; it += kDwThreads / 32) {
-    const int img = it / nstrips, w0 = (it - img * nstrips) * SW;
-    const float* xb = x + (int64_t)img * H * W * C + c;
-    const float* db = dy + (int64_t)img * H * W * C + c;
-    float dyr[5][SW];
-#pragma unroll
-    for (int r = -2; r < H; ++r) {
-      if (r + 2 < H) {  // dy row r + 2 enters the window (rows 0 and 1 on the two lead-in steps)
-#pragma unroll
-        for (int j = 0; j < SW; ++j) {
-          const float v = (w0 + j < W) ? __ldg(db + (int64_t)((r + 2) * W + w0 + j) * C) : 0.f;
-          dyr[(r + 2) % 5][j] = v;
-          acc[25] += v;
-        }
-      }
-      if (r < 0) continue;
-      float xr[SW + 4];
-#pragma unroll
-      for (int j = 0; j < SW + 4; ++j) {
-        const int wc = w0 - 2 + j;
-        float v = 0.f;
-        if (wc >= 0 && wc < W) {
-          v = __ldg(xb + (int64_t)(r * W + wc) * C);
-          if (activate) v = act_fwd_rt(fmaf(v, sc, sh), act);
-        }
-        xr[j] = v;
-      }
-#pragma unroll
-      for (int tr = 0; tr < 5; ++tr) {
-        const int h = r + 2 - tr;
-        if (h < 0 || h >= H) continue;
-#pragma unroll
-        for (int sx = 0; sx < 5; ++sx)
-#pragma unroll
-          for (int j = 0; j < SW; ++j) acc[tr * 5 + sx] = fmaf(xr[j + sx], dyr[h % 5][j], acc[tr * 5 + sx]);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 26; ++i) red[warp][i][lane] = acc[i];
-  __syncthreads();
-  for (int i = threadIdx.x; i < 26 * kDwCC; i += kDwThreads) {
-    float s2 = 0.f;
-#pragma unroll
-    for (int wv = 0; wv < kDwThreads / 32; ++wv) s2 += red[wv][i / kDwCC][i % kDwCC];
-    partial[((int64_t)blockIdx.y * 26 + i / kDwCC) * C + blockIdx.x * kDwCC + (i % kDwCC)] = s2;
-  }
-}
-
-// (H, strip width) instantiations: 4x4 and 8x8 (the model), 7x7 / 14x14 (BASELINE configs[1]), 16x16
-struct DwSlide { int H, SW, nstrips; };
-static bool dw_slide_geom(int H, int W, DwSlide* g) {
-  if (H != W) return false;
-  if (H == 4) { *g = {4, 4, 1}; return true; }
-  if (H == 7) { *g = {7, 7, 1}; return true; }
-  if (H == 8) { *g = {8, 8, 1}; return true; }
-  if (H == 14) { *g = {14, 7, 2}; return true; }
-  if (H == 16) { *g = {16, 8, 2}; return true; }
-  return false;
-}
-// backward-filter: CTAs (= partials) per channel chunk, ~3 CTAs per SM in total, at least one item per warp
-static int dw_slide_filter_groups(int nitems, int nchunks) {
-  int64_t g = ceil_div(3 * kNumSMs, nchunks);
-  const int64_t cap = ceil_div(nitems, kDwThreads / 32);
-  if (g > cap) g = cap;
-  return (int)(g < 1 ? 1 : g);
-}
-static bool dw_slide_enabled() {  // NVAE_DW_SLIDE=0: the staged shared-memory kernels (A/B measurements)
-  const char* e = getenv("NVAE_DW_SLIDE");
-  return !(e != nullptr && e[0] == '0');
-}
-
 static int dw_check(int N, int H, int W, int C) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % kDwCC)) return NVAE_E_BADSHAPE;
   DwGeom g = dw_geom(N, H, W, C);
@@ -562,25 +395,6 @@ using namespace nvae;
 template <bool FLIP>
 static int dw_launch(const float* x, const float* stat, int act, int N, int H, int W, int C, const float* w,
                      const float* bias, float* y, cudaStream_t stream) {
-  DwSlide sl;
-  if (dw_slide_enabled() && dw_slide_geom(H, W, &sl)) {
-    const int nitems = N * sl.nstrips, nchunks = C / kDwCC, wpc = kDwThreads / 32;
-    int ipw = (int)((int64_t)nitems * nchunks / ((int64_t)wpc * 4 * kNumSMs));  // ~4 CTAs per SM in total
-    ipw = ipw < 1 ? 1 : (ipw > 8 ? 8 : ipw);
-    const dim3 grid(nchunks, (unsigned)ceil_div(nitems, (int64_t)wpc * ipw));
-#define NVAE_DW_SLIDE(H_, SW_)                                                                                         \
-  nvae::launch(dw_slide_kernel<H_, SW_, FLIP>, grid, kDwThreads, 0, stream, x, stat, act, N, W, C, w, bias, y, sl.nstrips, ipw)
-    switch (sl.H) {
-      case 4: NVAE_DW_SLIDE(4, 4); break;
-      case 7: NVAE_DW_SLIDE(7, 7); break;
-      case 8: NVAE_DW_SLIDE(8, 8); break;
-      case 14: NVAE_DW_SLIDE(14, 7); break;
-      default: NVAE_DW_SLIDE(16, 8); break;
-    }
-#undef NVAE_DW_SLIDE
-    NVAE_RETURN_IF_LAUNCH_FAILED();
-    return NVAE_OK;
-  }
   DwGeom g = dw_geom(N, H, W, C);
   if (!FLIP) {  // forward: one tile per CTA, activation in registers
     const size_t smem1 = g.smem_tile * sizeof(float);
@@ -628,13 +442,7 @@ extern "C" int nvae_dwconv5x5_bwd_data(const float* dy, int N, int H, int W, int
 extern "C" size_t nvae_dwconv5x5_bwd_filter_ws_bytes(int N, int H, int W, int C) {
   if (dw_check(N, H, W, C)) return 0;
   DwGeom g = dw_geom(N, H, W, C);
-  size_t groups = (size_t)g.ngroups;
-  DwSlide sl;
-  if (dw_slide_geom(H, W, &sl)) {
-    const size_t sg = (size_t)dw_slide_filter_groups(N * sl.nstrips, C / kDwCC);
-    if (sg > groups) groups = sg;
-  }
-  return groups * 26 * C * sizeof(float);
+  return (size_t)g.ngroups * 26 * C * sizeof(float);
 }
 
 extern "C" int nvae_dwconv5x5_bwd_filter(const float* x, const float* stat, int act, const float* dy, int N, int H,
@@ -643,29 +451,6 @@ extern "C" int nvae_dwconv5x5_bwd_filter(const float* x, const float* stat, int 
   int rc = dw_check(N, H, W, C);
   if (rc) return rc;
   if (!x || !dy || !dw) return NVAE_E_NULLPTR;
-  DwSlide sl;
-  if (dw_slide_enabled() && dw_slide_geom(H, W, &sl)) {
-    const int nitems = N * sl.nstrips, nchunks = C / kDwCC;
-    const int groups = dw_slide_filter_groups(nitems, nchunks);
-    if (ws == nullptr || ws_bytes < (size_t)groups * 26 * C * sizeof(float)) return NVAE_E_WORKSPACE;
-    float* partial = reinterpret_cast<float*>(ws);
-    const int ipc = (int)ceil_div(nitems, groups);
-    const dim3 grid(nchunks, (unsigned)ceil_div(nitems, ipc));
-#define NVAE_DW_SLIDE_F(H_, SW_)                                                                                       \
-  nvae::launch(dw_slide_filter_kernel<H_, SW_>, grid, kDwThreads, 0, stream, x, stat, act, dy, N, W, C, partial, sl.nstrips, ipc)
-    switch (sl.H) {
-      case 4: NVAE_DW_SLIDE_F(4, 4); break;
-      case 7: NVAE_DW_SLIDE_F(7, 7); break;
-      case 8: NVAE_DW_SLIDE_F(8, 8); break;
-      case 14: NVAE_DW_SLIDE_F(14, 7); break;
-      default: NVAE_DW_SLIDE_F(16, 8); break;
-    }
-#undef NVAE_DW_SLIDE_F
-    NVAE_RETURN_IF_LAUNCH_FAILED();
-    nvae::launch(dwconv5x5_bwd_filter_reduce_kernel, (26 * C + 255) / 256, 256, 0, stream, partial, (int)grid.y, C, dw, dbias);
-    NVAE_RETURN_IF_LAUNCH_FAILED();
-    return NVAE_OK;
-  }
   DwGeom g = dw_geom(N, H, W, C);
   if (ws == nullptr || ws_bytes < (size_t)g.ngroups * 26 * C * sizeof(float)) return NVAE_E_WORKSPACE;
   size_t dfloats = (size_t)g.imgs * H * W * kDwCC;

@@ -175,6 +175,7 @@ class NVAE:
             enc_dec_combiners.reverse()  # flip bottom-up to top-down
             reconstruction, z_params, log_p, log_q = self.decoder(final_x, enc_dec_combiners, nll=nll,
                                                                   training=training)
+            self._post_mark = len(rt.tape) if rt.tape is not None else None  # first tape entry of the postprocess tower
             reconstruction = self.postprocess(reconstruction, training)
         finally:
             if did_sn:
@@ -203,7 +204,7 @@ class NVAE:
             self._counters[0] = int(metric)
         self._host_metric = metric
 
-    def train_step(self, data, apply_gradients: bool = True) -> Dict[str, torch.Tensor]:
+    def train_step(self, data, apply_gradients: bool = True, _on_bucket=None) -> Dict[str, torch.Tensor]:
         """One training step.  Returns the reference's dict (models.py:130-135) of DEVICE tensors:
         loss [], reconstruction_loss [B], kl_loss [B], bn_loss []."""
         if isinstance(data, tuple):
@@ -233,7 +234,7 @@ class NVAE:
         reconstruction.grad = rt.empty(N, H, W, Cl)
         rt.lib.bernoulli_ll_bwd(reconstruction.ptr(), data.ptr(), N, H, W, data.shape[3], Cl, 1.0 / B,
                                 reconstruction.grad.data_ptr(), rt.stream)
-        rt.backward(tape)
+        rt.backward(tape, split_at=self._post_mark if _on_bucket is not None else None, on_split=_on_bucket)
         if rt.bn_loss_n:
             rt.lib.bn_loss_bwd(rt.params.data_ptr(), rt.grads.data_ptr(), rt.bn_loss_offsets.data_ptr(),
                                rt.bn_loss_sizes.data_ptr(), rt.bn_loss_n, float(self.sr_lambda), rt.stream)
@@ -249,11 +250,18 @@ class NVAE:
         rt = self.rt
         if self.optimizer is None:
             raise RuntimeError("call compile(optimizer=Adamax(...)) before training")
-        world = 1
+        world = self._world()
+        if world > 1:
+            torch.distributed.all_reduce(rt.grads, group=self.process_group)
+        self._adamax(world)
+
+    def _world(self) -> int:
         if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            world = torch.distributed.get_world_size(self.process_group)
-            if world > 1:
-                torch.distributed.all_reduce(rt.grads, group=self.process_group)
+            return torch.distributed.get_world_size(self.process_group)
+        return 1
+
+    def _adamax(self, world: int) -> None:
+        rt = self.rt
         opt = self.optimizer
         rt.lib.adamax(rt.params.data_ptr(), rt.grads.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
                       rt.params.numel(), self._hyper.data_ptr(), opt.beta_1, opt.beta_2, opt.epsilon, 1.0 / world,
@@ -309,8 +317,31 @@ class NVAE:
             hasattr(torch.cuda.CUDAGraph, "raw_cuda_graph")
         graph = torch.cuda.CUDAGraph(keep_graph=True) if node_prio else torch.cuda.CUDAGraph()
         launches0, kernels0 = rt.lib.launches, rt.lib._nvae_launch_count()
-        with torch.cuda.graph(graph, stream=stream):
-            out = self.train_step(static_in, apply_gradients=in_graph)
+        # More than one rank: the step is TWO graphs.  The first ends when backward has left the postprocess tower (the tail
+        # of the gradient arena, 35 % of the parameters, produced first); its bucket is all-reduced on NCCL's stream while
+        # the second graph -- the rest of backward -- runs, so only the second bucket's exchange is exposed
+        # (NVAE_DP_OVERLAP=0: one graph, one all-reduce after it).
+        overlap = (not in_graph) and os.environ.get("NVAE_DP_OVERLAP", "1") != "0"
+        graph2 = None
+        if overlap:
+            graph2 = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(rt.device)
+            with torch.cuda.stream(stream):
+                graph.capture_begin()
+
+                def next_graph():
+                    graph.capture_end()
+                    graph2.capture_begin(pool=graph.pool())
+                try:
+                    out = self.train_step(static_in, apply_gradients=False, _on_bucket=next_graph)
+                finally:
+                    (graph2 if self._post_mark is not None else graph).capture_end()
+            torch.cuda.current_stream(rt.device).wait_stream(stream)
+            post0 = next(v.offset for v in rt.trainable_variables if v.name.startswith("postprocess/"))
+            self._dp_buckets = (rt.grads[post0:], rt.grads[:post0])
+        else:
+            with torch.cuda.graph(graph, stream=stream):
+                out = self.train_step(static_in, apply_gradients=in_graph)
         graph_exec = None
         if node_prio:
             import ctypes
@@ -320,6 +351,7 @@ class NVAE:
                 raise _lib.NvaeError(f"nvae_graph_instantiate failed: cudaError_t {rc}")
             graph_exec = ex
             self._graph_exec = (ex, rt.lib)  # kept alive with the model
+        self._graph2 = graph2
         self.graph_kernels = rt.lib._nvae_launch_count() - kernels0 + (0 if in_graph else 1)  # + Adamax outside
         self.steps -= 1  # capture records the launches without running them
         self._host_metric = self.steps if self.step_based_warmup else self.epoch
@@ -334,9 +366,16 @@ class NVAE:
                 rc = rt.lib._nvae_graph_launch(graph_exec, rt.stream)
                 if rc != 0:
                     raise _lib.NvaeError(f"nvae_graph_launch failed: cudaError_t {rc}")
+            elif graph2 is not None:
+                graph.replay()
+                first = torch.distributed.all_reduce(self._dp_buckets[0], group=self.process_group, async_op=True)
+                graph2.replay()
+                torch.distributed.all_reduce(self._dp_buckets[1], group=self.process_group)
+                first.wait()
+                self._adamax(world)
             else:
                 graph.replay()
-            if not in_graph:
+            if not in_graph and graph2 is None:
                 self.apply_gradients()
             self.steps += 1
             if self.step_based_warmup:

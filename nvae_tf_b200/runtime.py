@@ -313,9 +313,17 @@ class Runtime:
         finally:
             self._last_tape, self.tape = self.tape, prev
 
-    def backward(self, tape: List[Callable[[], None]]) -> None:
-        for fn in reversed(tape):
-            fn()
+    def backward(self, tape: List[Callable[[], None]], split_at: Optional[int] = None,
+                 on_split: Optional[Callable[[], None]] = None) -> None:
+        """Replays the tape in reverse.  `split_at` (a tape index) / `on_split`: once every closure recorded at or after
+        that index has run -- and the weight-gradient side stream has been joined, so those layers' gradients are final --
+        `on_split()` is called; the data-parallel step uses it to end one CUDA graph and begin the next, so the first
+        gradient bucket can be all-reduced while the rest of backward runs."""
+        for i in range(len(tape) - 1, -1, -1):
+            if split_at is not None and on_split is not None and i == split_at - 1:
+                self.join_side_stream()
+                on_split()
+            tape[i]()
         self.join_side_stream()
         tape.clear()
 

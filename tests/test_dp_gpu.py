@@ -59,15 +59,30 @@ def _worker(rank, world, port, q):
         for _ in range(3):
             m.train_step(x[sl])
         torch.cuda.synchronize()
+        # the same 3 steps through the CAPTURED path bench.py times at N > 1: two graphs, the postprocess bucket all-reduced
+        # while the second graph runs -- must land on bit-identical parameters (Philox is counter-keyed, sums of two ranks
+        # commute)
+        g = NVAE(**H.mirror_kwargs(cfg, GB // world), training=True, seed=1)
+        g.compile(optimizer=Adamax(learning_rate=CosineDecay(1e-3, 1000)))
+        g.rt.load_named(params)
+        g.steps = m.steps - 3        # the eager model took its 3 optimizer steps from here ...
+        g._counters[1] = 1           # ... and from optimizer iteration 1 (the gradient-only step above advanced it)
+        static_in, replay = g.capture_train_step((GB // world, 32, 32, 1))
+        assert g._graph2 is not None, "overlapped two-graph step expected with more than one rank"
+        static_in.copy_(torch.as_tensor(np.asarray(x[sl], np.float32)))
+        for _ in range(3):
+            replay()
+        torch.cuda.synchronize()
+        graph_equals_eager = bool(torch.equal(g.rt.params, m.rt.params))
         p = m.rt.params.double()
         mine = torch.stack([p.sum(), (p * p).sum(), p.abs().max()]).cpu()
         allv = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allv, mine)
-        q.put((rank, worst, [int(t.item()) for t in seeds], [t.tolist() for t in allv]))
+        q.put((rank, worst, [int(t.item()) for t in seeds], [t.tolist() for t in allv], graph_equals_eager))
         dist.barrier()
         dist.destroy_process_group()
     except Exception as e:  # surface the failure instead of a queue timeout
-        q.put((rank, ("exception: " + repr(e), 1e9), [], []))
+        q.put((rank, ("exception: " + repr(e), 1e9), [], [], False))
         raise
 
 
@@ -83,7 +98,8 @@ def test_two_replicas_average_to_the_oracle_and_stay_identical(lib_built):
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, worst, seeds, sums in res:
+    for rank, worst, seeds, sums, graph_ok in res:
         assert worst[1] <= 1e-3, worst                 # averaged gradient == oracle's 2-replica emulation
+        assert graph_ok                                # overlapped two-graph replay == eager steps, bit for bit
         assert seeds[0] != seeds[1]                    # the ranks draw different epsilons
         assert sums[0] == sums[1]                      # identical parameters on both ranks after 3 optimizer steps
