@@ -10,6 +10,12 @@ and writes an .npz with the layout of tests/golden/*.npz (`param/`, `eps/`, `los
 
     python tools/dump_tf_golden.py /path/to/nvae-tf tests/golden/tf_tiny_train.npz
 
+Environment to run it in (the reference's own pins, requirements.txt:41-42, plus the two packages it imports but does not
+pin -- the releases that pair with TensorFlow 2.3):
+    python 3.8
+    pip install tensorflow==2.3.0 tensorflow-estimator==2.3.0 numpy==1.18.5 scipy==1.4.1 \
+                tensorflow-addons==0.11.2 tensorflow-probability==0.11.1
+
 NOT RUN in the build image (no TensorFlow wheel, no network): DESIGN.md section 5 therefore says
 "parity unpinned".  The variable-name mapping below follows the attribute paths the reference's checkpoints
 use, which is also how nvae_tf_b200 names its variables.
