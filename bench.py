@@ -197,7 +197,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # roofline of the dominant kernel, measured live
 # ------------------------------------------------------------------------------------------
-def dominant_traffic(f16, x3):
+def dominant_traffic(f16, x3, two=False):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch from the committed `ncu --set full` summary
     (profiles/dominant_kernel_traffic.json), valid only for the conv_tc.cu revision it was captured from: when the
     kernel source changed since, the reading is stale and `traffic` is reported as null."""
@@ -207,7 +207,7 @@ def dominant_traffic(f16, x3):
         src = open(os.path.join(ROOT, "nvae_tf_b200", "csrc", "conv_tc.cu"), "rb").read()
     except OSError:
         return None, "profiles/dominant_kernel_traffic.json missing"
-    key = "f16x3" if f16 else ("tf32x3" if x3 else None)
+    key = ("f16x2" if two else "f16x3") if f16 else ("tf32x3" if x3 else None)
     ent = rec.get(key) if key else None
     if ent is None:
         return None, "no capture for this arithmetic"
@@ -436,19 +436,25 @@ def main():
     x3 = precision == _lib.NVAE_PREC_TF32X3
     # NVAE_PREC_TF32X3 runs its large GEMMs (this one included) as 3xFP16 on kind::f16 unless NVAE_F16X3=0
     f16 = x3 and os.environ.get("NVAE_F16X3", "1") != "0"
+    # ... and, unless NVAE_F16X2=0, with the two-term product (B rounded to fp16) for those >= 20 GFLOP launches
+    two = f16 and os.environ.get("NVAE_F16X2", "1") != "0"
+    mmas = 2 if two else (3 if x3 else 1)
     bf16_peak = peaks.get("bf16_tflops", 1590.0)
     # kind::f16 runs at the dense bf16/fp16 rate (the measured cuBLAS figure); kind::tf32 at half of it (nominal ratio)
     peak = bf16_peak if f16 else bf16_peak / 2.0
     achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
-    arith = ("3xFP16: amax-scaled fp16 hi/lo split, A via TMEM, pre-split B via TMA, two accumulators per CTA" if f16 else
+    arith = ("2-term 3xFP16 (A hi/lo x B rounded to fp16): amax-scaled, A via TMEM, pre-split B via TMA, two accumulators per CTA"
+             if two else
+             "3xFP16: amax-scaled fp16 hi/lo split, A via TMEM, pre-split B via TMA, two accumulators per CTA" if f16 else
              "3xTF32 split in-kernel, A via TMEM" if x3 else "single-pass TF32")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 # algorithmic bytes are 127.9 MB (x + w + y once)
-                "traffic": dominant_traffic(f16, x3)[0], "traffic_source": dominant_traffic(f16, x3)[1],
-                "mma_issue_factor": 3 if x3 else 1,
-                "issued_mma_frac": (3 if x3 else 1) * achieved / peak,
-                "note": ("fp32-grade products cost 3 MMAs each (hi*hi + hi*lo + lo*hi), so the ceiling of frac is 1/3; "
-                         "issued_mma_frac is the tensor pipe's own utilisation against the same peak") if x3 else "",
+                "traffic": dominant_traffic(f16, x3, two)[0], "traffic_source": dominant_traffic(f16, x3, two)[1],
+                "mma_issue_factor": mmas,
+                "issued_mma_frac": mmas * achieved / peak,
+                "note": (f"split-operand products cost {mmas} MMAs each, so the ceiling of frac is 1/{mmas}; issued_mma_frac is "
+                         "the tensor pipe's own utilisation against the same peak (the kernel runs at the MMA issue rate the "
+                         "1 kW power cap allows: sw_power_cap is the only throttle reason)") if x3 else "",
                 "kernel": ("conv_tc_kernel<false> (tcgen05 " + ("kind::f16" if f16 else "kind::tf32") +
                            " implicit GEMM, TMA-staged, " + arith + ")" +
                            (" + absmax2_kernel + f16_pack_b_kernel (operand scales / B split, inside ms_per_launch)" if f16 else "")
@@ -466,7 +472,9 @@ def main():
         extra = side_measurements(precision)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": ("f16x3+tf32x3" if f16 else "tf32x3" if x3 else "tf32") if tc else "f32", "data": "synthetic",
+            "vs_baseline": None,
+            "dtype": ("f16x2+tf32x3" if two else "f16x3+tf32x3" if f16 else "tf32x3" if x3 else "tf32") if tc else "f32",
+            "data": "synthetic",
             "config": {"workload": CFG["workload"],
                        "batch_per_gpu": B, "global_batch": B * world, "image": f"32x32x{CFG['channels']}",
                        "parameters": int(model.rt.n_trainable()),

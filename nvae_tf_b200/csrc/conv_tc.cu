@@ -310,8 +310,8 @@ struct TcParams {
                                 // [hi 32 x fp16 | lo 32 x fp16] per 32-deep K chunk that TMA drops into the raw ring) and multiplied
                                 // as hi*hi + hi*lo + lo*hi with kind::f16 -- the same 22 significant bits per operand
                                 // as 3xTF32 at twice the tensor-pipe rate; the epilogue undoes the scales
-  int f16_terms;                // 3 (default): hi*hi + hi*lo + lo*hi.  2 (experiment, NVAE_F16X2=1): the A_hi*B_lo term is not
-                                // issued, i.e. B enters rounded to fp16 (11 significant bits) -- 2/3 of the MMAs
+  int f16_terms;                // 3: hi*hi + hi*lo + lo*hi.  2 (the >= 20 GFLOP launches unless NVAE_F16X2=0): the A_hi*B_lo term is
+                                // not issued, i.e. B enters rounded to fp16 (11 significant bits) -- 2/3 of the MMAs
   const float* amax;            // device: {absmax(A operand), absmax(B operand)}, written just before the launch
   int dual;                     // 3xFP16: a CTA tile is TWO 128-row M tiles (mt = 2*(t / n_ntiles) + g) that share every
                                 // staged B tile: stage = [A0][A1][B], converter group g splits A_g, accumulator g at column
@@ -1579,10 +1579,17 @@ bool use_f16x3(const NvaeConvDesc* d, int which) {
   return gflop >= min_gflop;
 }
 
-// Experiment: two-term product for the 3xFP16 GEMMs, NVAE_F16X2=1.  Off by default.
-bool f16_two_terms() {
+// Two-term product for the LARGE 3xFP16 GEMMs (>= 20 GFLOP per launch: the six 5x5 convolutions of the postprocess tower,
+// whatever NVAE_F16X3_MIN_GFLOP says): A_hi*B_hi + A_lo*B_hi, i.e. the B operand (weights; dY for backward-filter) enters
+// rounded to nearest fp16 of its amax-scaled value -- 11 significant bits, unbiased.  These GEMMs run at the MMA issue rate
+// under the power cap, so 2/3 of the MMAs is the only thing that makes them faster (0.573 -> 0.528 ms).  Adopted on the
+// measured whole-step parity at batch 144 (tests/test_step_b144_gpu.py: worst gradient tensor 2.8e-4, median 9.6e-6 against
+// the fp32 CUDA-core path; three-term: 5.8e-5 / 8.0e-6; bound 1e-3).  NVAE_F16X2=0 restores the three-term product.
+bool f16_two_terms(const NvaeConvDesc* d) {
   const char* e = getenv("NVAE_F16X2");
-  return e != nullptr && e[0] == '1';
+  if (e != nullptr && e[0] == '0') return false;
+  const double gflop = 2.0 * d->N * d->Ho * d->Wo * (double)d->Cout * (d->Cin + d->Cin2) * d->R * d->S * 1e-9;
+  return gflop >= 20.0;
 }
 
 // which: 0 forward, 1 dgrad; ntaps: K-loop taps (a stride-2 dgrad launch covers one output parity class)
@@ -1674,7 +1681,7 @@ void fill_common(TcParams* p, const NvaeConvDesc* d, const Plan& pl, float* part
   p->a5d = 0; p->par_c = d->Cin;
   p->tw = pl.t.tw; p->th = pl.t.th; p->tn = pl.t.tn; p->tiles_h = pl.t.tiles_h;
   p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->acc_bufs = pl.acc_bufs; p->pair = pl.pair || pl.dual; p->dual = pl.dual; p->n_mtiles = pl.n_mtiles; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1; p->f16 = pl.f16; p->amax = nullptr; p->nsub = pl.nsub;
-  p->f16_terms = f16_two_terms() ? 2 : 3;
+  p->f16_terms = (pl.f16 && f16_two_terms(d)) ? 2 : 3;
   p->n_ntiles = pl.n_ntiles; p->KU = pl.KU; p->U = pl.U;
   p->T = ((pl.pair || pl.dual) ? (pl.n_mtiles + 1) / 2 : pl.n_mtiles) * pl.n_ntiles; p->whole_tiles = pl.whole_tiles;
   p->a_bytes = pl.a_bytes; p->b_bytes = pl.b_bytes;

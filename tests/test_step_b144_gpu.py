@@ -53,10 +53,14 @@ def _rel(a: torch.Tensor, b: torch.Tensor, floor: float) -> float:
     return float((a.double() - b.double()).abs().max() / max(float(b.double().abs().max()), floor))
 
 
-def test_batch144_graph_replay_matches_fp32_cuda_core_path(lib_built, monkeypatch):
+@pytest.mark.parametrize("large_gemm_product", ["two-term (default)", "three-term (NVAE_F16X2=0)"])
+def test_batch144_graph_replay_matches_fp32_cuda_core_path(lib_built, monkeypatch, large_gemm_product):
     from nvae_tf_b200 import _lib
     monkeypatch.delenv("NVAE_F16X3_MIN_GFLOP", raising=False)
     monkeypatch.delenv("NVAE_F16X3", raising=False)
+    monkeypatch.delenv("NVAE_F16X2", raising=False)
+    if large_gemm_product.startswith("three"):
+        monkeypatch.setenv("NVAE_F16X2", "0")
     x = _images()
     # --- the benchmarked path: default arithmetic (3xFP16 for the six large GEMMs, 3xTF32 elsewhere), graph replay
     m = _model()
@@ -101,7 +105,7 @@ def test_batch144_graph_replay_matches_fp32_cuda_core_path(lib_built, monkeypatc
             continue
         errs.append((_rel(a, b, 1e-4 * gmax), n))
     errs.sort(reverse=True)
-    print("batch-144 gradients, tensor-core graph replay vs fp32 CUDA cores: worst", errs[:5],
+    print(f"batch-144 gradients, tensor-core graph replay [{large_gemm_product}] vs fp32 CUDA cores: worst", errs[:5],
           "median %.2e over %d tensors" % (errs[len(errs) // 2][0], len(errs)))
     assert errs[0][0] <= TOL, errs[:5]
     for n, off, size in snames:  # BN moving statistics, SN u
@@ -113,6 +117,7 @@ def test_batch144_graph_replay_matches_fp32_cuda_core_path(lib_built, monkeypatc
 
 def test_batch144_losses_match_float64_oracle(lib_built, monkeypatch):
     monkeypatch.delenv("NVAE_F16X3_MIN_GFLOP", raising=False)
+    monkeypatch.delenv("NVAE_F16X2", raising=False)
     cfg = O.NVAEConfig()
     params, trainable, bnl, s = O.build_params(cfg, seed=1, jitter=0.05)
     params = {k: np.asarray(v * (GAMMA if k.endswith("/gamma") else 1.0), np.float32).astype(np.float64)
