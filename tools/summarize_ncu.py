@@ -52,7 +52,10 @@ def short(name):
 
 def main():
     rep = sys.argv[1]
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # `ncu -i x.ncu-rep --page raw --csv > x.csv` exported on the GPU box
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     head, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(head)}
@@ -64,8 +67,8 @@ def main():
     print("| kernel | grid x block | regs | smem KB | us | DRAM MB | GB/s | of HBM | dram% | L2% | SM% | tensor% | occupancy% | top stalls |")
     print("|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|")
     for r in data:
-        if len(r) < len(head):
-            continue
+        if len(r) < len(head) or r[col["Kernel Name"]].lstrip("void ").startswith("at::"):
+            continue  # (torch's own fill / randn kernels of the driver script)
         g = {}
         for m, k in WANT.items():
             if m in col:
@@ -76,7 +79,7 @@ def main():
                 if v is not None and k in ("rd", "wr"):
                     v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
                 if v is not None and k in ("dsmem", "ssmem"):
-                    v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6}.get(u, 1)
+                    v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6}.get(u.split("/")[0], 1)
                 g[k] = v
         stalls = []
         for h, i in col.items():
@@ -97,7 +100,7 @@ def main():
         us = g.get("us") or 0
         gbs = mb * 1e6 / (us * 1e-6) / 1e9 if us else 0
         f = lambda k, p=1: (f"{g[k]:.{p}f}" if g.get(k) is not None else "-")
-        smem = ((g.get("dsmem") or 0) + (g.get("ssmem") or 0)) / 1024
+        smem = ((g.get("dsmem") or 0) + (g.get("ssmem") or 0)) / 1000
         print(f"| `{short(r[col['Kernel Name']])}` | {f('grid', 0)} x {f('block', 0)} | {f('regs', 0)} | {smem:.0f} | {us:.1f} | "
               f"{mb:.1f} | {gbs:.0f} | {100 * gbs / HBM:.0f}% | {f('dram%')} | {f('l2%')} | {f('sm%')} | {f('tensor%')} | {f('occ%')} | "
               f"{', '.join(top)} |")
