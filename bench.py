@@ -480,7 +480,10 @@ def main():
                        "parameters": int(model.rt.n_trainable()),
                        "parallelism": f"dp{world}", "training_mode": "batch-stat BN + SN power iteration",
                        "l2": "per-step working set ~6 GB of activations >> 126 MB L2 (no explicit flush needed)",
-                       "execution": "one CUDA graph per step" + ("" if world == 1 else " + NCCL all-reduce + Adamax")},
+                       "execution": ("one CUDA graph per step" if world == 1 else
+                                     "two CUDA graphs per step: the postprocess gradient bucket is all-reduced (NCCL) under the second "
+                                     "graph, then the second bucket + Adamax" if getattr(model, "_graph2", None) is not None else
+                                     "one CUDA graph per step + NCCL all-reduce + Adamax")},
             "e2e": e2e, "gpu_launches": model.graph_kernels * args.steps, "kernels_per_step": model.graph_kernels,
             "launcher_calls_per_step": model.graph_launches,
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "final_loss": loss, "e2e_loss": res["loss"],
