@@ -28,7 +28,8 @@
 // SM, at most 148), so every SM gets the same number of pipeline stages whatever the tile count; a CTA
 // that covers only part of a tile's K range writes its raw accumulator to a partial buffer and a fix-up
 // kernel sums the partials of each split tile in CTA order (deterministic) and applies the epilogue.
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer (warp 14: a second issuer that takes
+// the second accumulator of the two-accumulator 3xFP16 tiles -- the issuing thread, not the tensor pipe, paces those kernels),
 // warps 2..9 = lo-part converters, warps 10..13 = epilogue (tcgen05.ld -> bias / residual / accumulate ->
 // 128-bit stores) on a double-buffered TMEM accumulator, so the next tile's MMAs overlap the drain.
 #include <cuda.h>
@@ -47,7 +48,8 @@ constexpr int kChunk = 32;       // fp32 elements per 128-byte swizzle row
 constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 256;                   // warps 2..9: lo-part converters (3xTF32)
 constexpr int kEpiThreads = 128;                    // warps 10..13: epilogue, one per TMEM lane group
-constexpr int kThreads = 64 + kConvThreads + kEpiThreads;
+constexpr int kIssue2Warp = (64 + kConvThreads + kEpiThreads) / 32;  // warp 14: second MMA issuer (two-accumulator 3xFP16 tiles)
+constexpr int kThreads = 64 + kConvThreads + kEpiThreads + 32;
 constexpr int kSmemBudget = 208 * 1024;  // operand rings; the epilogue staging (17 KB) and barriers come on top
 
 // ------------------------------------------------------------------------------------------------
@@ -310,6 +312,7 @@ struct TcParams {
                                 // [hi 32 x fp16 | lo 32 x fp16] per 32-deep K chunk that TMA drops into the raw ring) and multiplied
                                 // as hi*hi + hi*lo + lo*hi with kind::f16 -- the same 22 significant bits per operand
                                 // as 3xTF32 at twice the tensor-pipe rate; the epilogue undoes the scales
+  int issue2;                   // two MMA-issuing threads for two-accumulator 3xFP16 tiles (NVAE_TC_ISSUE2=0: one)
   int f16_terms;                // 3: hi*hi + hi*lo + lo*hi.  2 (the >= 20 GFLOP launches unless NVAE_F16X2=0): the A_hi*B_lo term is
                                 // not issued, i.e. B enters rounded to fp16 (11 significant bits) -- 2/3 of the MMAs
   const float* amax;            // device: {absmax(A operand), absmax(B operand)}, written just before the launch
@@ -519,17 +522,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   if (threadIdx.x == 0) {
     TC_STAMP(0);
+    // two MMA issuers (3xFP16 tiles with two accumulators): both commit every stage / A slot / accumulator
+    const uint32_t nissue = (!PAIR && p.f16 && (p.nsub == 2 || p.dual) && p.issue2) ? 2u : 1u;
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(smem_u32(&ctl->full[i]), 1);
-      mbar_init(smem_u32(&ctl->empty[i]), 1);
+      mbar_init(smem_u32(&ctl->empty[i]), nissue);
     }
     for (int i = 0; i < p.lo_stages; ++i) {
       // a_tmem: one 4-warp converter group per stage (PAIR: of both CTAs); else all 8 converter warps
       mbar_init(smem_u32(&ctl->conv[i]), (PAIR ? 2 : 1) * ((p.a_tmem && !p.dual) ? kConvThreads / 64 : kConvThreads / 32));
-      mbar_init(smem_u32(&ctl->lo_empty[i]), 1);
+      mbar_init(smem_u32(&ctl->lo_empty[i]), nissue);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&ctl->acc_full[i]), 1);
+      mbar_init(smem_u32(&ctl->acc_full[i]), nissue);
       mbar_init(smem_u32(&ctl->acc_empty[i]), (PAIR ? 2 : 1) * (kEpiThreads / 32));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -667,9 +672,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         u += kb - ka;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == kIssue2Warp) {
     // ---------------- MMA issuer (PAIR: the leader CTA only) ----------------
-    if (lane == 0 && (!PAIR || crank == 0)) {
+    // split: the tile has two accumulators (nsub / dual) and two issuing threads -- warp 1 issues the MMAs of the first,
+    // warp 14 those of the second; each waits on the stage's barriers and commits on its own.  One thread issuing all of a
+    // stage's MMAs costs it ~75 cycles per MMA plus ~600 cycles of waits, commits and loop overhead (in-kernel timeline:
+    // stage period 1 435 cycles against 768 of tensor-pipe time for the eight two-term MMAs).
+    const bool split = !PAIR && p.f16 && (p.nsub == 2 || p.dual) && p.issue2;
+    const int half = warp == kIssue2Warp ? 1 : 0;
+    if (lane == 0 && (!PAIR || crank == 0) && (half == 0 || split)) {
       const uint32_t idesc = WGRAD ? umma_idesc_tf32(p.BN, 1, 1) : umma_idesc_tf32(p.BN, 0, 0);
       // A from TMEM is K-major by construction; a pair MMA spans 256 rows
       const uint32_t idesc_ts = umma_idesc_tf32(p.BN, 0, WGRAD ? 1 : 0, PAIR ? 2 * kBM : kBM);
@@ -725,17 +736,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (f16) {
               // pre-split B row (TMA, raw ring): [hi k0..15 | hi k16..31 | lo k0..15 | lo k16..31], 32 bytes each
               TC_CYC(it, 8);
+              if (!split || half == 0) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + hk * j, idesc_h, accum | (j > 0));
-              TC_CYC(it, 9);
-              if (three) {
+                for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + hk * j, idesc_h, accum | (j > 0));
+                TC_CYC(it, 9);
+                if (three) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + hlo + hk * j, idesc_h, 1u);
+                  for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_hi + 8u * j, db + hlo + hk * j, idesc_h, 1u);
+                }
+                TC_CYC(it, 10);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_lo + 8u * j, db + hk * j, idesc_h, 1u);
               }
-              TC_CYC(it, 10);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) umma_f16_ts(acc, a_lo + 8u * j, db + hk * j, idesc_h, 1u);
-              if (p.dual) {  // the second M tile's A (slot columns 32..63) against the same B, into the second accumulator
+              if (p.dual && (!split || half == 1)) {  // the second M tile's A (slot columns 32..63) against the same B, into the second accumulator
                 const uint32_t acc2 = acc + (uint32_t)p.BN, b_hi = a_hi + 32u, b_lo = a_hi + 48u;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, b_hi + 8u * j, db + hk * j, idesc_h, accum | (j > 0));
@@ -746,7 +759,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
                 for (int j = 0; j < 2; ++j) umma_f16_ts(acc2, b_lo + 8u * j, db + hk * j, idesc_h, 1u);
               }
-              if (p.nsub == 2) {  // same A slot against the second B sub-tile, into the second accumulator
+              if (p.nsub == 2 && (!split || half == 1)) {  // same A slot against the second B sub-tile, into the second accumulator
                 const uint32_t acc2 = acc + (uint32_t)bns;
                 const uint64_t db2 = db + sub_step;
 #pragma unroll
@@ -1050,7 +1063,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int ab = seg % p.acc_bufs;
       mbar_wait(smem_u32(&ctl->acc_full[ab]), ((uint32_t)(seg / p.acc_bufs)) & 1u);
       tc_fence_after();
-      if (threadIdx.x == kThreads - 1) TC_STAMP(4);
+      if (threadIdx.x == kIssue2Warp * 32 - 1) TC_STAMP(4);
       for (int g = 0; g < (dual ? 2 : 1); ++g) {  // dual: accumulator g = M tile 2*(t / n_ntiles) + g
       const int mt = PAIR ? 2 * (t / p.n_ntiles) + (int)crank : dual ? 2 * (t / p.n_ntiles) + g : t / p.n_ntiles;
       const int hrank = PAIR ? (int)crank : g;
@@ -1094,7 +1107,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (PAIR) mbar_arrive_cluster(smem_u32(&ctl->acc_empty[ab]), 0);
         else mbar_arrive(smem_u32(&ctl->acc_empty[ab]));
       }
-      if (threadIdx.x == kThreads - 1) TC_STAMP(5);
+      if (threadIdx.x == kIssue2Warp * 32 - 1) TC_STAMP(5);
       u += kb - ka;
     }
   }
@@ -1682,6 +1695,10 @@ void fill_common(TcParams* p, const NvaeConvDesc* d, const Plan& pl, float* part
   p->tw = pl.t.tw; p->th = pl.t.th; p->tn = pl.t.tn; p->tiles_h = pl.t.tiles_h;
   p->BN = pl.BN; p->stages = pl.stages; p->lo_stages = pl.lo_stages; p->a_tmem = pl.a_tmem; p->acc_bufs = pl.acc_bufs; p->pair = pl.pair || pl.dual; p->dual = pl.dual; p->n_mtiles = pl.n_mtiles; p->passes = d->precision == NVAE_PREC_TF32X3 ? 3 : 1; p->f16 = pl.f16; p->amax = nullptr; p->nsub = pl.nsub;
   p->f16_terms = (pl.f16 && f16_two_terms(d)) ? 2 : 3;
+  {
+    const char* e = getenv("NVAE_TC_ISSUE2");
+    p->issue2 = !(e != nullptr && e[0] == '0');
+  }
   p->n_ntiles = pl.n_ntiles; p->KU = pl.KU; p->U = pl.U;
   p->T = ((pl.pair || pl.dual) ? (pl.n_mtiles + 1) / 2 : pl.n_mtiles) * pl.n_ntiles; p->whole_tiles = pl.whole_tiles;
   p->a_bytes = pl.a_bytes; p->b_bytes = pl.b_bytes;
