@@ -242,6 +242,16 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TC_STAMP(i) g_tc_timing[blockIdx.x * 16 + (i)] = gtime()
 __device__ long long g_tc_cyc[8 * 16];
 #define TC_CYC(it, j) do { if (blockIdx.x == 0 && (it) >= 8 && (it) < 16) g_tc_cyc[((it) - 8) * 16 + (j)] = clock64(); } while (0)
+// whole-launch totals for CTA 0, issuer 0: cycles waiting on full[] (TMA), on conv[] (converters), total loop cycles, units
+__device__ long long g_tc_wait[8];
+#define TC_WAIT_BEGIN() long long tcw_t0 = clock64(), tcw_a = 0, tcw_full = 0, tcw_conv = 0, tcw_n = 0
+#define TC_WAIT_A() tcw_a = clock64()
+#define TC_WAIT_FULL() do { const long long t_ = clock64(); tcw_full += t_ - tcw_a; tcw_a = t_; } while (0)
+#define TC_WAIT_CONV() do { const long long t_ = clock64(); tcw_conv += t_ - tcw_a; ++tcw_n; } while (0)
+#define TC_WAIT_END() do { if (blockIdx.x == 0 && half == 0) { g_tc_wait[0] = tcw_full; g_tc_wait[1] = tcw_conv; g_tc_wait[2] = clock64() - tcw_t0; g_tc_wait[3] = tcw_n; } } while (0)
+extern "C" __attribute__((visibility("default"))) int nvae_debug_tc_wait(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_tc_wait, sizeof(g_tc_wait));
+}
 extern "C" __attribute__((visibility("default"))) int nvae_debug_tc_cycles(long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_tc_cyc, sizeof(g_tc_cyc));
 }
@@ -251,6 +261,11 @@ extern "C" __attribute__((visibility("default"))) int nvae_debug_tc_timing(unsig
 #else
 #define TC_STAMP(i)
 #define TC_CYC(it, j)
+#define TC_WAIT_BEGIN()
+#define TC_WAIT_A()
+#define TC_WAIT_FULL()
+#define TC_WAIT_CONV()
+#define TC_WAIT_END()
 #endif
 
 struct SmemCtl {
@@ -704,6 +719,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const uint32_t conv0 = smem_u32(&ctl->conv[0]), loe0 = smem_u32(&ctl->lo_empty[0]);
         int st = 0, ls = 0, seg = 0, it = 0;
         uint32_t ph = 0, lph = 0, a_hi = a_base;
+        TC_WAIT_BEGIN();
         uint64_t db = b_desc0, lb = lb_desc0;
         (void)it;
         const bool f16 = !PAIR && p.f16;
@@ -726,10 +742,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           uint32_t accum = 0;
           for (int k = ka; k < kb; ++k, ++it) {
             TC_CYC(it, 13);
+            TC_WAIT_A();
             if (!PAIR) mbar_wait(full0 + 8u * st, ph);  // (PAIR: both CTAs' converters vouch for the tiles)
             TC_CYC(it, 0);
+            TC_WAIT_FULL();
             mbar_wait(conv0 + 8u * ls, lph);
             tc_fence_after();
+            TC_WAIT_CONV();
             TC_CYC(it, 1);
             if (it == 0) TC_STAMP(2);
             const uint32_t a_lo = a_hi + (f16 ? 16u : 32u);
@@ -810,6 +829,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           TC_STAMP(3);
           u += kb - ka;
         }
+        TC_WAIT_END();
       } else {
       int it = 0, seg = 0;
       for (int ph = 0; ph < so.n; ++ph)

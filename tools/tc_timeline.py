@@ -64,6 +64,12 @@ def main():
         print(f"rc={rc} event time {e0.elapsed_time(e1) * 1e3:.1f} us (incl. fix-up), {len(t)} CTAs; us since first CTA start:")
         for i, n in enumerate(names):
             print(f"  {n:11s} min {t[:, i].min():7.2f}  median {np.median(t[:, i]):7.2f}  max {t[:, i].max():7.2f}")
+        if hasattr(rt.lib.dll, "nvae_debug_tc_wait"):
+            wb = (C.c_longlong * 8)()
+            rt.lib.dll.nvae_debug_tc_wait(wb)
+            full, conv, total, n = wb[0], wb[1], wb[2], max(wb[3], 1)
+            print(f"CTA 0, issuer 0, whole launch: {n} k-units, {total / n:.0f} cycles per unit, of which waiting on full[] (TMA) "
+                  f"{full / n:.0f}, on conv[] (converters) {conv / n:.0f}")
         if hasattr(rt.lib.dll, "nvae_debug_tc_cycles"):
             cb = (C.c_longlong * 128)()
             rt.lib.dll.nvae_debug_tc_cycles(cb)
