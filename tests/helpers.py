@@ -61,7 +61,7 @@ def run_oracle_step(cfg, params_np, trainable, bn_in_loss, s, x_np, eps_np, step
     return losses, {k: v.detach().numpy() for k, v in grads.items()}, c, record
 
 
-def compare_grads(got: dict, want: dict, tol: float, zero_frac: float = 1e-9, noise_frac: float = 1e-5):
+def compare_grads(got: dict, want: dict, tol: float, zero_frac: float = 1e-9, noise_frac: float = 1e-5, report: str = ""):
     """Per-tensor max-rel-err of every gradient; returns (worst_name, worst_err).
 
     A bias that feeds a training-mode BatchNorm (conv1/bias -> batch_norm2, depth_conv/bias ->
@@ -71,15 +71,26 @@ def compare_grads(got: dict, want: dict, tol: float, zero_frac: float = 1e-9, no
     are instead required to stay below `noise_frac` of the largest gradient entry in the model."""
     gmax = max(float(np.abs(np.asarray(g)).max()) for g in want.values())
     worst = ("", 0.0)
+    zeros, floored = [], []
     for n, w in want.items():
         w = np.asarray(w, dtype=np.float64)
         g = np.asarray(got[n], dtype=np.float64)
-        if np.abs(w).max() <= zero_frac * gmax:
+        wmax = float(np.abs(w).max())
+        if wmax <= zero_frac * gmax:
             err = tol * float(np.abs(g).max()) / (noise_frac * gmax)  # == tol exactly at the noise bound
+            zeros.append(n)
         else:
             err = max_rel_err(g, w, 1e-4 * gmax)
+            if wmax < 1e-4 * gmax:  # the denominator floor (1e-4 of the largest gradient entry) is in effect: looser than
+                floored.append((n, 1e-4 * gmax / wmax, max_rel_err(g, w)))  # the plain per-tensor max|d| / max|ref|
         if err > worst[1]:
             worst = (n, err)
+    if report:
+        # the north star's plain criterion is per-tensor max|d| / max|ref| <= tol; say exactly where this check is looser
+        print(f"[{report}] {len(want)} gradient tensors: {len(zeros)} analytically zero (only bounded by {noise_frac:g} of the "
+              f"largest gradient entry), {len(floored)} compared with the denominator floor in effect:")
+        for n, factor, plain in sorted(floored, key=lambda t: -t[1]):
+            print(f"    {n}: floor loosens x{factor:.1f}; plain max|d|/max|ref| = {plain:.2e}")
     return worst
 
 

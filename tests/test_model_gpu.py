@@ -153,7 +153,7 @@ def test_default_config_step_against_live_oracle(lib_built, batch, steps, traini
     assert H.max_rel_err(npy(out["reconstruction_loss"]), losses["reconstruction_loss"]) < TOL_LOSS
     assert H.max_rel_err(npy(out["kl_loss"]), losses["kl_loss"], floor=1e-3) < TOL_LOSS
     assert H.max_rel_err(npy(m.decoder.sampler.kl_all), losses["kl_all"]) < TOL_LOSS
-    worst = H.compare_grads(m.rt.named_grads(), grads, TOL_ACT)
+    worst = H.compare_grads(m.rt.named_grads(), grads, TOL_ACT, report=f"default config, batch {batch}, f16x3={f16x3}")
     assert worst[1] < TOL_ACT, worst
     new = {k: v.detach().numpy() for k, v in c.new_stats.items()}
     for n, v in new.items():
