@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """How well-conditioned is the default-config NVAE step at batch 144?  Runs the oracle forward (training-mode BN, SN, injected
 epsilons) in torch-CPU float32 and float64 on the same weights / images / epsilons and prints how far the two drift apart.
-usage: python tools/conditioning_probe.py <gamma scale>      (1.0: Keras initial gamma; 0.3: the tests' operating point)
+usage: python tests/conditioning_probe.py <gamma scale>      (1.0: Keras initial gamma; 0.3: the tests' operating point)
 Measured here (8 host cores, ~7 min): gamma 1.0 -> loss 1.8e-4, kl_all 3.2e-4, logits 7.6e-4 (max |z| ~ 300);
 gamma 0.3 -> loss 4e-8, kl_all 5e-7, logits 8e-7.  The batch-144 parity tests therefore run at gamma = 0.3."""
 import sys, numpy as np, torch, time
 import os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 sys.path.insert(0, ROOT)
 from oracle import nvae_oracle as O
 torch.set_num_threads(8)

@@ -29,7 +29,7 @@ def _model(precision=None, seed=1, gamma=GAMMA):
     """Default-config model at the operating point the parity bound is meaningful at.  With Keras' initial gamma = 1 the
     untrained network is numerically chaotic at batch 144: sigma = exp(softclamp5(.)) saturates at e^5 = 148, z reaches
     +-300, and ANY two fp32 implementations disagree at the 1e-3 level -- torch-CPU fp32 vs the float64 oracle on this very
-    step: logits 7.6e-4, kl_all 3.2e-4 (tools/conditioning_probe.py).  With every BN gamma at 0.3 -- where the BN-gamma
+    step: logits 7.6e-4, kl_all 3.2e-4 (tests/conditioning_probe.py).  With every BN gamma at 0.3 -- where the BN-gamma
     regulariser of models.py:252-267 drives a trained model -- the same comparison gives logits 8e-7, kl_all 5e-7, so a
     1e-3 bound tests the arithmetic rather than the conditioning of a random network."""
     from nvae_tf_b200.models import NVAE, Adamax, CosineDecay
