@@ -73,3 +73,20 @@ def test_bucket_bounds_cover_the_arena_back_to_front():
     assert parallel.shard_batch(8, 1, 2) == slice(4, 8)
     with pytest.raises(ValueError):
         parallel.shard_batch(9, 0, 2)
+
+
+def test_bench_traffic_record_is_tied_to_the_kernel_source(tmp_path, monkeypatch):
+    """bench.py's roofline.traffic comes from profiles/dominant_kernel_traffic.json and is reported only while the hash of
+    conv_tc.cu recorded with the ncu capture still matches the source (no stale literal)."""
+    import hashlib
+    import json
+    import os
+    import bench
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rec = json.load(open(os.path.join(root, "profiles", "dominant_kernel_traffic.json")))
+    sha = hashlib.sha256(open(os.path.join(root, "nvae_tf_b200", "csrc", "conv_tc.cu"), "rb").read()).hexdigest()[:16]
+    assert rec["f16x2"]["conv_tc_sha16"] == sha, "conv_tc.cu changed since the ncu capture: re-capture or accept traffic = null"
+    val, src = bench.dominant_traffic(True, True, True)
+    assert val == rec["f16x2"]["dram_bytes"] and "r02_ncu_conv" in src
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))  # no profiles/ there -> no number, and it says why
+    assert bench.dominant_traffic(True, True, True)[0] is None
