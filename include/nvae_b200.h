@@ -242,6 +242,25 @@ NVAE_API int nvae_conv2d_dgrad(const NvaeConvDesc* d, const float* dy, const flo
 NVAE_API int nvae_conv2d_wgrad(const NvaeConvDesc* d, const float* x, const float* x2, const float* dy, float* dw,
                       float* dbias, void* ws, size_t ws_bytes, nvae_stream_t stream);
 
+/* The same convolution reading act(BN(x)) instead of x: the BatchNorm apply (x*scale[c]+shift[c], rows 2 and 3 of the
+ * [4][Cin] stat block nvae_bn_stats / nvae_bn_fwd wrote) and the activation run inside the tensor-core kernel's operand
+ * path (the warps that split the staged tile), forward and backward-filter, so the activated tensor is never written or
+ * re-read.  Replaces the BN -> (Swish) -> 1x1 Conv2D pairs: decoder.py:125-127 (batch_norm1 -> conv1), decoder.py:143-144
+ * (batch_norm3 + swish -> conv2), postprocess.py:71-73 (bn0 -> cbs1.conv), postprocess.py:84-96 (cbs2 BN + swish -> conv3).
+ * Backward-data is nvae_conv2d_dgrad as before (its result is the gradient of the ACTIVATED tensor; nvae_bn_act_bwd takes it
+ * from there).  Shapes: 1x1, stride 1, one source, Cin % 32 == 0, NVAE_PREC_TF32X3 below the 3xFP16 threshold --
+ * nvae_conv2d_bnact_supported says which; the launchers return NVAE_E_UNSUPPORTED otherwise (there is no second path behind
+ * them: the caller then applies the BN with nvae_bn_fwd and calls nvae_conv2d_fwd).  Workspace: nvae_conv2d_ws_bytes(d, 0 / 2).
+ * Results are bit-identical to nvae_bn_fwd + nvae_conv2d_fwd / _wgrad.  Measured on B200 the fused pair is SLOWER at the cells'
+ * sizes (the operand-splitting warps are those GEMMs' critical path), so the host mirror uses it only under
+ * NVAE_FUSE_BN_CONV=1|2. */
+NVAE_API int nvae_conv2d_bnact_supported(const NvaeConvDesc* d);
+NVAE_API int nvae_conv2d_fwd_bnact(const NvaeConvDesc* d, const float* x, const float* stat, int act, const float* w_tr,
+                          const float* bias, const float* residual, float* y, void* ws, size_t ws_bytes,
+                          nvae_stream_t stream);
+NVAE_API int nvae_conv2d_wgrad_bnact(const NvaeConvDesc* d, const float* x, const float* stat, int act, const float* dy,
+                            float* dw, float* dbias, void* ws, size_t ws_bytes, nvae_stream_t stream);
+
 /* Rounds a tensor in place to TF32 (round-to-nearest, ties away: cvt.rna.tf32.f32) so that a tensor-core
  * convolution consumes it without the truncation bias of feeding raw fp32 bits to kind::tf32.  Used on
  * conv operands whose producer did not already round them (gradients arriving at nvae_conv2d_dgrad/wgrad). */

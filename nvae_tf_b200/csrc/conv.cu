@@ -79,6 +79,42 @@ extern "C" int nvae_conv2d_wgrad(const NvaeConvDesc* d, const float* x, const fl
   return NVAE_OK;
 }
 
+// ---- convolution whose input is act(BN(x)): BN-apply + activation in the operand path ----------------------------
+extern "C" int nvae_conv2d_bnact_supported(const NvaeConvDesc* d) {
+  if (nvae_conv_check(d) != NVAE_OK || d->precision == NVAE_PREC_FP32) return 0;
+  return nvae_conv_tc_supported(d, 0) && nvae_conv_tc_supported(d, 2) && nvae_conv_tc_prolog_supported(d) ? 1 : 0;
+}
+
+extern "C" int nvae_conv2d_fwd_bnact(const NvaeConvDesc* d, const float* x, const float* stat, int act, const float* w_tr,
+                                     const float* bias, const float* residual, float* y, void* ws, size_t ws_bytes,
+                                     nvae_stream_t stream) {
+  int rc = nvae_conv_check(d);
+  if (rc) return rc;
+  if (!x || !stat || !w_tr || !y) return NVAE_E_NULLPTR;
+  if (act != NVAE_ACT_NONE && act != NVAE_ACT_SWISH && act != NVAE_ACT_ELU) return NVAE_E_BADSHAPE;
+  if (!nvae_conv2d_bnact_supported(d)) return NVAE_E_UNSUPPORTED;  // the caller applies the BN itself: no silent second path
+  return nvae_conv2d_fwd_tc(d, x, nullptr, w_tr, bias, residual, y, ws, ws_bytes, stream, stat, act);
+}
+
+extern "C" int nvae_conv2d_wgrad_bnact(const NvaeConvDesc* d, const float* x, const float* stat, int act,
+                                       const float* dy, float* dw, float* dbias, void* ws, size_t ws_bytes,
+                                       nvae_stream_t stream) {
+  int rc = nvae_conv_check(d);
+  if (rc) return rc;
+  if (!x || !stat || !dy || !dw) return NVAE_E_NULLPTR;
+  if (act != NVAE_ACT_NONE && act != NVAE_ACT_SWISH && act != NVAE_ACT_ELU) return NVAE_E_BADSHAPE;
+  if (!nvae_conv2d_bnact_supported(d)) return NVAE_E_UNSUPPORTED;
+  rc = nvae_conv2d_wgrad_tc(d, x, nullptr, dy, dw, ws, ws_bytes, stream, stat, act);
+  if (rc) return rc;
+  if (dbias != nullptr) {
+    const size_t off = align256(nvae_conv_tc_ws_bytes(d, 2));
+    if (ws == nullptr || ws_bytes < off + nvae_colsum_ws_bytes(d->Cout)) return NVAE_E_WORKSPACE;
+    return nvae_colsum(dy + d->y_off, (int64_t)d->N * d->Ho * d->Wo, d->Cout, d->y_ld > 0 ? d->y_ld : d->Cout, dbias,
+                       (char*)ws + off, ws_bytes - off, stream);
+  }
+  return NVAE_OK;
+}
+
 extern "C" int nvae_round_tf32(float* p, int64_t n, nvae_stream_t stream) {
   if (n > 0 && p == nullptr) return NVAE_E_NULLPTR;
   return nvae_round_tf32_inplace(p, n, stream);

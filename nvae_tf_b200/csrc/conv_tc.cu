@@ -366,6 +366,10 @@ struct TcParams {
   int KP;                       // pixels per stage (K extent)
   int pad_t, pad_l, njobs;      // job = (tap, 32-channel chunk); 4 jobs per M tile
   int Cin, Cin2, Ct, Cout;
+  // operand prolog (1x1 stride-1 forward / backward-filter, 3xTF32): the A operand is act(x * scale[c] + shift[c]),
+  // applied by the converter warps on the staged tile -- the activated tensor never exists in memory
+  const float* pro;             // scale[pro_C] followed by shift[pro_C] (rows 2, 3 of a BatchNorm stat block), or nullptr
+  int pro_C, pro_act;
 };
 
 // ---- stream-K partition (identical arithmetic in every role and in the fix-up kernel) -----------------
@@ -515,7 +519,9 @@ __device__ __forceinline__ void f16_split8(const float4& v0, const float4& v1, f
 // stages its own 128 pixel rows of A (-> its TMEM) and HALF of the B tile (BN/2 weight rows) in its shared memory, the
 // leader issues the MMAs for both SMs.  Per SM this halves the B bytes moved by TMA, split by the converters and
 // read by the MMAs -- the shared-memory port, not the tensor pipe, is what bounds the single-CTA kernel.
-template <bool WGRAD, bool PAIR>
+// PRO: the operand prolog (TcParams::pro) is compiled in.  A separate instantiation: even unused, its code in the converter
+// loop cost every 3xTF32 launch ~2 % (measured: 29.8 -> 30.5 ms per step), the converters being on the critical path.
+template <bool WGRAD, bool PAIR, bool PRO = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TmapSet maps, const TcParams p) {
   nvae::pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -930,6 +936,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         int st = it0 % p.stages, ls = it0 % p.lo_stages;
         uint32_t ph = (uint32_t)(it0 / p.stages) & 1u, lph = (uint32_t)(it0 / p.lo_stages) & 1u;
         const float f16_sa = p.f16 ? f16_in_scale(__ldg(p.amax)) : 1.f;
+        constexpr bool pro = PRO && !PAIR;
         for (int it = it0; it < n_units; it += itstep) {
           if (gt == 0) TC_CYC(it, 3);
           mbar_wait(smem_u32(&ctl->lo_empty[ls]), lph ^ 1u);
@@ -984,6 +991,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           const uint32_t ta = tmem + (uint32_t)(p.acc_bufs * p.BN) + (uint32_t)ls * 64u + ((uint32_t)((warp & 3) * 32) << 16);
           uint32_t hi[16], lw[16];
+          // operand prolog: first channel this thread's values belong to (forward: the unit's K chunk; backward-filter:
+          // the (job, lane) channel of the tile, constant over the pixel sweep)
+          int pc = 0;
+          float psc = 1.f, psh = 0.f;
+          if (pro) {
+            const long long len0 = so.hi[0] - so.lo[0];
+            const long long u = it < len0 ? so.lo[0] + it : so.lo[1] + (it - len0);
+            const int t = (int)(u / p.KU);
+            if (!WGRAD) {
+              pc = (((int)(u - (long long)t * p.KU)) % nch) * kChunk;
+            } else {
+              pc = ((t / p.n_ntiles * 4 + (warp & 3)) % nch) * kChunk + lane;
+              psc = __ldg(p.pro + pc);
+              psh = __ldg(p.pro + p.pro_C + pc);
+            }
+          }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {  // K columns [16*half, +16) of this thread's TMEM lane
             if (!WGRAD) {
@@ -992,7 +1015,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               const float4* arow = reinterpret_cast<const float4*>(raw + m * 128);
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const float4 v = arow[(half * 4 + c) ^ (m & 7)];
+                float4 v = arow[(half * 4 + c) ^ (m & 7)];
+                if (pro) {
+                  const float4 sc = nvae::ldg4(p.pro + pc + 4 * (half * 4 + c));
+                  const float4 sh = nvae::ldg4(p.pro + p.pro_C + pc + 4 * (half * 4 + c));
+                  v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                  v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                  if (p.pro_act == NVAE_ACT_SWISH) {
+                    v.x = act_fwd<NVAE_ACT_SWISH>(v.x); v.y = act_fwd<NVAE_ACT_SWISH>(v.y);
+                    v.z = act_fwd<NVAE_ACT_SWISH>(v.z); v.w = act_fwd<NVAE_ACT_SWISH>(v.w);
+                  } else if (p.pro_act == NVAE_ACT_ELU) {
+                    v.x = act_fwd<NVAE_ACT_ELU>(v.x); v.y = act_fwd<NVAE_ACT_ELU>(v.y);
+                    v.z = act_fwd<NVAE_ACT_ELU>(v.z); v.w = act_fwd<NVAE_ACT_ELU>(v.w);
+                  }
+                }
                 const float4 l = tf32_lo4(v);
                 hi[4 * c] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
                 hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
@@ -1006,7 +1042,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
               for (int kk = 0; kk < 16; ++kk) {
                 const int k = half * 16 + kk;
-                const float v = box[k * 32 + ((((lane >> 3) ^ (k & 3)) << 3) | (lane & 7))];
+                float v = box[k * 32 + ((((lane >> 3) ^ (k & 3)) << 3) | (lane & 7))];
+                if (pro) {  // (pixels beyond the batch become act(shift), and meet zero dY rows)
+                  v = fmaf(v, psc, psh);
+                  if (p.pro_act == NVAE_ACT_SWISH) v = act_fwd<NVAE_ACT_SWISH>(v);
+                  else if (p.pro_act == NVAE_ACT_ELU) v = act_fwd<NVAE_ACT_ELU>(v);
+                }
                 hi[kk] = __float_as_uint(v);
                 lw[kk] = __float_as_uint(tf32_lo(v));
               }
@@ -1745,16 +1786,16 @@ int f16_prepare(TcParams* p, const Plan& pl, const float* a, int64_t na, const f
   return NVAE_OK;
 }
 
-template <bool WGRAD, bool PAIR>
+template <bool WGRAD, bool PAIR, bool PRO = false>
 int launch_main(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<WGRAD, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<WGRAD, PAIR, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
   if (!PAIR) {
-    nvae::launch(conv_tc_kernel<WGRAD, PAIR>, pl.G, kThreads, pl.smem, stream, maps, p);
+    nvae::launch(conv_tc_kernel<WGRAD, PAIR, PRO>, pl.G, kThreads, pl.smem, stream, maps, p);
     NVAE_RETURN_IF_LAUNCH_FAILED();
     return NVAE_OK;
   }
@@ -1777,7 +1818,9 @@ int launch_main(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStre
 
 template <bool WGRAD>
 int launch(const TmapSet& maps, const TcParams& p, const Plan& pl, cudaStream_t stream) {
-  int rc = (!WGRAD && pl.pair) ? launch_main<false, true>(maps, p, pl, stream) : launch_main<WGRAD, false>(maps, p, pl, stream);
+  int rc = (!WGRAD && pl.pair) ? launch_main<false, true>(maps, p, pl, stream)
+           : p.pro != nullptr  ? launch_main<WGRAD, false, true>(maps, p, pl, stream)
+                               : launch_main<WGRAD, false>(maps, p, pl, stream);
   if (rc) return rc;
   if (pl.split) {
     FixList fl;
@@ -1851,11 +1894,24 @@ size_t nvae_conv_tc_ws_bytes(const NvaeConvDesc* d, int which) {
   return plan_gemm(d, which, d->R * d->S, &pl) ? pl.part_bytes : 0;
 }
 
+// The operand prolog (A = act(BN(x)) applied by the converter warps) exists for the shapes the cells need it for: 1x1,
+// stride 1, one source, whole 32-channel chunks, 3xTF32 with A in TMEM, unpaired CTAs.
+bool nvae_conv_tc_prolog_supported(const NvaeConvDesc* d) {
+  if (d->precision != NVAE_PREC_TF32X3 || d->R != 1 || d->S != 1 || d->stride != 1 || d->Cin2 != 0 || d->Cin % kChunk != 0)
+    return false;
+  Plan f, g;
+  if (!plan_gemm(d, 0, 1, &f) || !plan_wgrad(d, &g)) return false;
+  if (f.f16 || f.pair || f.dual || g.f16 || g.pair || g.dual || !g.a_tmem) return false;
+  return wgrad_chunks(d) == 1;
+}
+
 int nvae_conv2d_fwd_tc(const NvaeConvDesc* d, const float* x, const float* x2, const float* w_tr, const float* bias,
-                       const float* residual, float* y, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                       const float* residual, float* y, void* ws, size_t ws_bytes, cudaStream_t stream,
+                       const float* pro_stat, int pro_act) {
   Plan pl;
   const int Ct = d->Cin + d->Cin2, taps = d->R * d->S;
   if (!plan_gemm(d, 0, taps, &pl)) return NVAE_E_UNSUPPORTED;
+  if (pro_stat && !nvae_conv_tc_prolog_supported(d)) return NVAE_E_UNSUPPORTED;
   if (!aligned16(x) || !aligned16(x2) || !aligned16(w_tr) || !aligned16(bias) || !aligned16(residual) || !aligned16(y) ||
       !aligned16(ws))
     return NVAE_E_UNSUPPORTED;
@@ -1883,6 +1939,7 @@ int nvae_conv2d_fwd_tc(const NvaeConvDesc* d, const float* x, const float* x2, c
   p.out1 = y; p.out2 = nullptr;
   p.ld1 = d->y_ld > 0 ? d->y_ld : d->Cout; p.off1 = d->y_off; p.ld2 = 0;
   p.bias = bias; p.res = residual; p.accumulate = 0;
+  if (pro_stat) { p.pro = pro_stat + 2 * (size_t)d->Cin; p.pro_C = d->Cin; p.pro_act = pro_act; }
   TmapSet maps;
   int rc;
   if (d->stride == 2)
@@ -1978,12 +2035,14 @@ static int wgrad_chunks(const NvaeConvDesc* d) {
 }
 
 static int wgrad_tc_once(const NvaeConvDesc* d, const float* x, const float* x2, const float* dy, float* dw, void* ws,
-                         size_t ws_bytes, cudaStream_t stream, int accumulate);
+                         size_t ws_bytes, cudaStream_t stream, int accumulate, const float* pro_stat = nullptr,
+                         int pro_act = 0);
 
 int nvae_conv2d_wgrad_tc(const NvaeConvDesc* d, const float* x, const float* x2, const float* dy, float* dw, void* ws,
-                         size_t ws_bytes, cudaStream_t stream) {
+                         size_t ws_bytes, cudaStream_t stream, const float* pro_stat, int pro_act) {
   const int nc = wgrad_chunks(d);
-  if (nc == 1) return wgrad_tc_once(d, x, x2, dy, dw, ws, ws_bytes, stream, 0);
+  if (pro_stat && !nvae_conv_tc_prolog_supported(d)) return NVAE_E_UNSUPPORTED;
+  if (nc == 1) return wgrad_tc_once(d, x, x2, dy, dw, ws, ws_bytes, stream, 0, pro_stat, pro_act);
   NvaeConvDesc s = *d;
   s.N = d->N / nc;
   const int ld = d->y_ld > 0 ? d->y_ld : d->Cout;
@@ -1996,7 +2055,7 @@ int nvae_conv2d_wgrad_tc(const NvaeConvDesc* d, const float* x, const float* x2,
 }
 
 static int wgrad_tc_once(const NvaeConvDesc* d, const float* x, const float* x2, const float* dy, float* dw, void* ws,
-                         size_t ws_bytes, cudaStream_t stream, int accumulate) {
+                         size_t ws_bytes, cudaStream_t stream, int accumulate, const float* pro_stat, int pro_act) {
   Plan pl;
   if (!plan_wgrad(d, &pl)) return NVAE_E_UNSUPPORTED;
   if (!aligned16(x) || !aligned16(x2) || !aligned16(dy) || !aligned16(dw) || !aligned16(ws)) return NVAE_E_UNSUPPORTED;
@@ -2014,6 +2073,7 @@ static int wgrad_tc_once(const NvaeConvDesc* d, const float* x, const float* x2,
   p.out1 = dw;
   p.accumulate = accumulate;
   p.a5d = d->stride == 2;
+  if (pro_stat) { p.pro = pro_stat + 2 * (size_t)d->Cin; p.pro_C = d->Cin; p.pro_act = pro_act; }
   TmapSet maps;
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   int rc;

@@ -123,11 +123,10 @@ class GenerativeResidualCell(Layer):
 
     def __call__(self, inputs: DeviceTensor, training: bool = False) -> DeviceTensor:
         rt = self.rt
-        x = R.bn_act(rt, inputs, self.batch_norm1, NVAE_ACT_NONE, training)  # no activation after BN1
-        x = self.conv1(x, training)
+        # BN1 (no activation) and BN3 + swish are applied inside the 1x1 convolutions that consume them
+        x = self.conv1(inputs, training, bn_in=(self.batch_norm1, NVAE_ACT_NONE, training))
         x = R.dwconv_bn_act(rt, x, self.batch_norm2, NVAE_ACT_SWISH, self.depth_conv, training)
-        x = R.bn_act(rt, x, self.batch_norm3, NVAE_ACT_SWISH, training)
-        x = self.conv2(x, training)
+        x = self.conv2(x, training, bn_in=(self.batch_norm3, NVAE_ACT_SWISH, training))
         return self.se.fused(x, inputs, 0.1, 1.0, bn=self.batch_norm4, training=training)
 
     call = __call__

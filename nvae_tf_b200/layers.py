@@ -62,9 +62,14 @@ class Conv2D(Layer):
             return self.rt.pack[self.rnd_off:].data_ptr()
         return self.kernel.ptr() if self.tr_off >= 0 else None
 
-    def __call__(self, x: DeviceTensor, x2=None, residual=None, **kw) -> DeviceTensor:
+    def __call__(self, x: DeviceTensor, x2=None, residual=None, bn_in=None, **kw) -> DeviceTensor:
+        """bn_in=(bn, act, training): the input is act(bn(x)), applied inside the convolution where the kernel can."""
         if self.sn is None and self.tr_off >= 0 and not self.rt.sn_done:
             self.rt.pack_plain(self)  # un-wrapped conv (tests): refresh the operand copies on every call
+        if bn_in is not None:
+            if x2 is not None or kw:
+                raise NotImplementedError("bn_in with a second source / shifted view")
+            return R.bn_conv2d(self.rt, x, bn_in[0], bn_in[1], self, bn_in[2], residual=residual)
         return R.conv2d(self.rt, x, self, x2=x2, residual=residual, **kw)
 
 

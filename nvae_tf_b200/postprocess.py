@@ -69,9 +69,11 @@ class ConvBNSwish(Layer):
                        in_channels=in_channels, name="conv"))
             self.bn = BatchNormalization(momentum=0.05, epsilon=1e-5, channels=n_channels, name="bn")
 
-    def __call__(self, x: DeviceTensor, training: bool = False) -> DeviceTensor:
-        x = self.conv(x, training)
-        return R.bn_act(self.rt, x, self.bn, NVAE_ACT_SWISH, training)
+    def __call__(self, x: DeviceTensor, training: bool = False, bn_in=None, defer: bool = False) -> DeviceTensor:
+        """bn_in: a BatchNorm (+ activation) in front of the conv, applied inside it; defer: return the raw conv output --
+        the caller hands (self.bn, swish) to the next 1x1 convolution as ITS bn_in."""
+        x = self.conv(x, training, bn_in=bn_in) if bn_in is not None else self.conv(x, training)
+        return x if defer else R.bn_act(self.rt, x, self.bn, NVAE_ACT_SWISH, training)
 
     call = __call__
 
@@ -97,10 +99,9 @@ class PostprocessNode(Layer):
     def __call__(self, inputs: DeviceTensor, skipped: DeviceTensor, training: bool = False) -> DeviceTensor:
         rt = self.rt
         x = inputs if self.rescaler is None else self.rescaler(inputs, training)
-        x = R.bn_act(rt, x, self.bn0, NVAE_ACT_NONE, training)
-        x = self.cbs1(x, training)
-        x = self.cbs2(x, training)
-        x = self.conv3(x, training)
+        x = self.cbs1(x, training, bn_in=(self.bn0, NVAE_ACT_NONE, training))
+        x = self.cbs2(x, training, defer=True)
+        x = self.conv3(x, training, bn_in=(self.cbs2.bn, NVAE_ACT_SWISH, training))
         return self.se.fused(x, skipped, 1.0, 0.1, bn=self.bn1, training=training)
 
     call = __call__

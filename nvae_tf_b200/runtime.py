@@ -118,6 +118,10 @@ class Runtime:
         self._side_dirty = False
         self._keepalive: List[torch.Tensor] = []
         # single-pass TF32 rounds gradients in place before use, which a concurrent reader must not see half-done
+        # BN-apply (+ activation) of the BN -> 1x1 conv pairs inside the convolution's operand path (bn_conv2d)
+        # 0 (default): never; 1: a BN without activation (an FMA per element); 2: also BN + swish / ELU.  Off by default:
+        # the converter warps that would apply it are the critical path of these small GEMMs
+        self.fuse_bn_conv = int(os.environ.get("NVAE_FUSE_BN_CONV", "0"))
         self.use_side_stream = (os.environ.get("NVAE_WGRAD_STREAM", "1") != "0" and
                                 self.precision != _lib.NVAE_PREC_TF32 and self.device.type == "cuda")
         self.sn_done = False
@@ -605,6 +609,50 @@ def conv2d(rt: Runtime, x: DeviceTensor, conv, x2: Optional[DeviceTensor] = None
                 rt.add_grad(residual, dy, take=out is None and not rt.use_side_stream)
             if out is None:
                 y.grad = None
+        rt.record(bwd)
+    return y
+
+
+def bn_conv2d(rt: Runtime, x: DeviceTensor, bn, act: int, conv, training: bool,
+              residual: Optional[DeviceTensor] = None) -> DeviceTensor:
+    """conv(act(BN(x))) (+ bias, + residual) for the BN -> [Swish] -> 1x1 Conv2D pairs of the cells (decoder.py:125-127,
+    143-144; postprocess.py:71-73, 84-96).  Where the kernel takes it (nvae_conv2d_bnact_supported) the BN-apply and the
+    activation can run in the operand path of the tensor-core convolution, forward and backward-filter: one statistics
+    launch and the convolution, the activated tensor is never written (NVAE_FUSE_BN_CONV=1: BN without activation, 2: all).
+    Bit-identical to, and measured SLOWER than, bn_act followed by conv2d (31.1 / 32.6 against 29.8 ms per step: the
+    converter warps are these GEMMs' critical path, the activation is redone per N tile and again in backward-filter),
+    so the default (0) is the unfused pair."""
+    k = conv.kernel
+    d = conv_desc(rt, x.shape, 0, k.shape, conv.stride)
+    from ._lib import NVAE_ACT_NONE
+    if rt.fuse_bn_conv < (1 if act == NVAE_ACT_NONE else 2) or not rt.lib._nvae_conv2d_bnact_supported(C.byref(d)):
+        return conv2d(rt, bn_act(rt, x, bn, act, training), conv, residual=residual)
+    stat = bn_stats(rt, x, bn, training)
+    y = DeviceTensor(rt.empty(d.N, d.Ho, d.Wo, d.Cout))
+    ws, wsb = rt.workspace(rt.lib._nvae_conv2d_ws_bytes(C.byref(d), 0))
+    bias = conv.bias
+    rt.lib.conv2d_fwd_bnact(C.byref(d), x.ptr(), stat.data_ptr(), act, conv.packed_fwd(),
+                            bias.ptr() if bias is not None else None, residual.ptr() if residual is not None else None,
+                            y.ptr(), ws, wsb, rt.stream)
+    if rt.tape is not None:
+        def bwd():
+            dy = y.grad
+            if dy is None:
+                raise RuntimeError(f"conv {k.name}: output has no gradient")
+            with rt.side_stream():
+                ws, wsb = rt.workspace(rt.lib._nvae_conv2d_ws_bytes(C.byref(d), 2))
+                rt.lib.conv2d_wgrad_bnact(C.byref(d), x.ptr(), stat.data_ptr(), act, dy.data_ptr(), k.gptr(),
+                                          bias.gptr() if bias is not None else None, ws, wsb, rt.stream)
+            rt.keep_alive(dy)
+            rt.keep_alive(stat)
+            da = rt.empty(*x.shape)  # gradient of the activated tensor, consumed by the BN backward right below
+            ws, wsb = rt.workspace(rt.lib._nvae_conv2d_ws_bytes(C.byref(d), 1))
+            rt.lib.conv2d_dgrad(C.byref(d), dy.data_ptr(), k.ptr(), conv.packed_dgrad(), da.data_ptr(), None, 0, ws, wsb,
+                                rt.stream)
+            if residual is not None:
+                rt.add_grad(residual, dy, take=not rt.use_side_stream)
+            _bn_backward(rt, da, x, stat, bn, act, (0, 0), training)
+            y.grad = None
         rt.record(bwd)
     return y
 

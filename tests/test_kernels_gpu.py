@@ -267,6 +267,88 @@ def test_conv2d_tensor_core_modes(lib_built, case, mode, tol, monkeypatch):
         check("db", npy(conv.bias.grad), bo.grad.numpy(), tol)
 
 
+BN_CONV_CASES = [  # (N, H, W, Cin, Cout, act, residual, bias): the BN -> [swish] -> 1x1 conv pairs of the cells
+    (9, 16, 16, 32, 192, 0, False, True),     # decoder conv1 (BN1, no activation)
+    (9, 16, 16, 192, 32, 1, False, True),     # decoder conv2 (BN3 + swish)
+    (5, 4, 4, 768, 128, 1, True, True),       # deep K, ragged pixel tiles (80 pixels), residual epilogue
+    (3, 32, 32, 192, 32, 1, False, False),    # postprocess conv3 (cbs2 BN + swish), no bias
+    (7, 8, 8, 64, 384, 0, False, False),      # postprocess cbs1.conv behind bn0
+    (144, 4, 4, 256, 1536, 0, False, True),   # bench-size group-0 decoder cell: split-K plans on both launches
+    (144, 4, 4, 1536, 256, 2, False, True),   # ... and ELU, for the third activation code
+]
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("case", BN_CONV_CASES)
+def test_bn_conv2d_operand_prolog(lib_built, case, training, monkeypatch):
+    """conv(act(BN(x))) with the BN-apply + activation inside the convolution's operand path (nvae_conv2d_fwd_bnact /
+    _wgrad_bnact): against the float64 oracle, and bit for bit against the unfused pair (bn_fwd writes the activated
+    tensor, conv2d reads it) -- both feed the same fp32 values to the same tile arithmetic."""
+    import ctypes as C
+    from nvae_tf_b200 import _lib
+    from nvae_tf_b200 import runtime as R
+    from nvae_tf_b200.layers import BatchNormalization, Conv2D
+    N, Hh, W, Cin, Cout, act, residual, use_bias = case
+    rng = np.random.default_rng(11)
+    w = f32(rng.normal(0, 1.0 / np.sqrt(Cin), (1, 1, Cin, Cout)))
+    b = f32(rng.normal(0, 0.3, Cout))
+    vals = {"gamma": rng.normal(1, 0.2, Cin), "beta": rng.normal(0, 0.3, Cin), "moving_mean": rng.normal(0, 0.5, Cin),
+            "moving_variance": rng.uniform(0.5, 2, Cin)}
+    x = f32(rng.normal(0.5, 2.0, (N, Hh, W, Cin)))
+    res = f32(rng.normal(0, 1, (N, Hh, W, Cout))) if residual else None
+    dy = f32(rng.normal(0, 1, (N, Hh, W, Cout)))
+    got = {}
+    for fused in ("2", "0"):
+        monkeypatch.setenv("NVAE_FUSE_BN_CONV", fused)
+        with R.Runtime(seed=7, precision=_lib.NVAE_PREC_TF32X3) as rt:
+            bn = BatchNormalization(momentum=0.05, epsilon=1e-5, channels=Cin, name="bn")
+            conv = Conv2D(Cout, (1, 1), padding="same", use_bias=use_bias, in_channels=Cin, name="c")
+            rt.finalize()
+            for k, v in vals.items():
+                getattr(bn, k).assign(v)
+            conv.kernel.assign(w)
+            if use_bias:
+                conv.bias.assign(b)
+            xt = dev(rt, x)
+            d = R.conv_desc(rt, xt.shape, 0, conv.kernel.shape, 1)
+            assert rt.lib._nvae_conv2d_bnact_supported(C.byref(d)) == 1, "this shape must take the fused path"
+            with rt.gradient_tape() as tape:
+                y = conv(xt, residual=dev(rt, res) if residual else None, bn_in=(bn, act, training))
+            seed_grad(rt, y, dy)
+            rt.backward(tape)
+            torch.cuda.synchronize()
+            got[fused] = dict(y=y.data.clone(), dx=xt.grad.clone(), dw=conv.kernel.grad.clone(),
+                              db=conv.bias.grad.clone() if use_bias else None, dgamma=bn.gamma.grad.clone(),
+                              dbeta=bn.beta.grad.clone(), mm=bn.moving_mean.value.clone(),
+                              mv=bn.moving_variance.value.clone())
+    for k in got["2"]:
+        if got["2"][k] is not None:
+            assert torch.equal(got["2"][k], got["0"][k]), f"{k}: fused and unfused differ"
+    # oracle
+    p = {"bn/" + k: H.t64(f32(v)) for k, v in vals.items()}
+    p["bn/gamma"].requires_grad_(True)
+    p["bn/beta"].requires_grad_(True)
+    c = O.Ctx(p, training)
+    xo = H.t64(x).requires_grad_(True)
+    wo, bo = H.t64(w).requires_grad_(True), H.t64(b).requires_grad_(True)
+    yo = O.conv2d(ACTS[act](O.batch_norm(c, "bn", xo)), wo, bo if use_bias else None, 1)
+    if residual:
+        yo = yo + H.t64(res)
+    yo.backward(H.t64(dy))
+    g = got["2"]
+    tol = 5e-5
+    check("y", npy(g["y"]), yo.detach().numpy(), tol)
+    check("dx", npy(g["dx"]), xo.grad.numpy(), tol)
+    check("dw", npy(g["dw"]), wo.grad.numpy(), tol)
+    if use_bias:
+        check("db", npy(g["db"]), bo.grad.numpy(), tol)
+    check("dgamma", npy(g["dgamma"]), p["bn/gamma"].grad.numpy(), tol)
+    check("dbeta", npy(g["dbeta"]), p["bn/beta"].grad.numpy(), tol)
+    if training:
+        check("moving_mean", npy(g["mm"]), c.new_stats["bn/moving_mean"].numpy())
+        check("moving_variance", npy(g["mv"]), c.new_stats["bn/moving_variance"].numpy())
+
+
 @pytest.mark.parametrize("shape", [(144, 16, 16, 384, 384), (144, 32, 32, 192, 192)])
 def test_conv2d_full_size_3xfp16_agrees_with_3xtf32(lib_built, shape, monkeypatch):
     """BASELINE-size check of the dominant GEMMs (batch 144; the float64 oracle would need minutes per case): the 3xFP16

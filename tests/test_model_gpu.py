@@ -308,6 +308,25 @@ def test_cuda_graph_replay_equals_eager(lib_built):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_bn_apply_inside_the_1x1_convolutions_is_the_same_step(lib_built, mode, monkeypatch):
+    """NVAE_FUSE_BN_CONV (opt-in): the BN-apply (1) and BN + swish (2) in front of the cells' 1x1 convolutions run in the
+    convolution's operand path.  Same values into the same tile arithmetic: three optimizer steps end bit-identical to
+    the default step."""
+    cfg = H.oracle_cfg()
+    x = torch.as_tensor(O.make_images(cfg, 4, seed=3).numpy().astype(np.float32))
+    res = []
+    for fuse in ("0", mode):
+        monkeypatch.setenv("NVAE_FUSE_BN_CONV", fuse)
+        m = _make_model(cfg, 4, True, seed=5)
+        for _ in range(3):
+            out = m.train_step(x.cuda())
+        torch.cuda.synchronize()
+        res.append((out["loss"].item(), m.rt.params.clone(), m.rt.state.clone()))
+    assert res[0][0] == res[1][0]
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+
+
 def test_graph_replay_follows_epoch_based_warmup(lib_built):
     """train.py default: --step_based_warmup off, beta = min(epoch / (0.3 n_total), 1) moves only in on_epoch_begin
     (models.py:121-122).  The replayed graph must see the new epoch (it used to keep the capture-time beta)."""

@@ -144,6 +144,75 @@ class NvaeConv2dWgradOp : public OpKernel {
 REGISTER_KERNEL_BUILDER(Name("NvaeConv2dWgrad").Device(DEVICE_GPU), NvaeConv2dWgradOp);
 
 // ------------------------------------------------------------------------------------------------
+// BN -> [swish] -> 1x1 Conv2D with the BN-apply + activation inside the convolution (decoder.py:125-127, 143-144;
+// postprocess.py:71-73, 84-96).  stat is the [4, Cin] block of NvaeBnStats / NvaeBnFwd.  The launcher refuses shapes
+// the fused operand path does not take (rc = NVAE_E_UNSUPPORTED): nvae_tf_layers.bn_conv2d checks
+// nvae_conv2d_bnact_supported first and composes bn_act + conv2d otherwise.
+// ------------------------------------------------------------------------------------------------
+REGISTER_OP("NvaeConv2dFwdBnact")
+    .Input("x: float").Input("stat: float").Input("w: float").Input("w_tr: float").Input("bias: float")
+    .Input("residual: float")
+    .Attr("act: int = 1").Attr("precision: int = 2")
+    .Output("y: float");
+
+class NvaeConv2dFwdBnactOp : public OpKernel {
+ public:
+  explicit NvaeConv2dFwdBnactOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("act", &act_));
+    OP_REQUIRES_OK(c, c->GetAttr("precision", &precision_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &x = ctx->input(0), &stat = ctx->input(1), &w = ctx->input(2), &w_tr = ctx->input(3),
+                 &bias = ctx->input(4), &res = ctx->input(5);
+    const NvaeConvDesc d = conv_desc(x.dim_size(0), x.dim_size(1), x.dim_size(2), x.dim_size(3), 0, w.dim_size(3),
+                                     w.dim_size(0), w.dim_size(1), 1, precision_);
+    OP_REQUIRES(ctx, nvae_conv2d_bnact_supported(&d) == 1,
+                errors::InvalidArgument("NvaeConv2dFwdBnact: shape not on the fused path; use NvaeBnFwd + NvaeConv2dFwd"));
+    Tensor* y = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({d.N, d.Ho, d.Wo, d.Cout}), &y));
+    Tensor ws;
+    const size_t ws_bytes = nvae_conv2d_ws_bytes(&d, 0);
+    OP_REQUIRES_OK(ctx, alloc_ws(ctx, ws_bytes, &ws));
+    const int rc = nvae_conv2d_fwd_bnact(&d, fptr(x), fptr(stat), act_, fptr(w_tr), fptr(bias), fptr(res), fptr(y),
+                                         ws.flat<uint8>().data(), ws_bytes, stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_conv2d_fwd_bnact failed: ", rc));
+  }
+ private:
+  int act_, precision_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeConv2dFwdBnact").Device(DEVICE_GPU), NvaeConv2dFwdBnactOp);
+
+REGISTER_OP("NvaeConv2dWgradBnact")
+    .Input("x: float").Input("stat: float").Input("dy: float")
+    .Attr("act: int = 1").Attr("precision: int = 2")
+    .Output("dw: float").Output("dbias: float");
+
+class NvaeConv2dWgradBnactOp : public OpKernel {
+ public:
+  explicit NvaeConv2dWgradBnactOp(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("act", &act_));
+    OP_REQUIRES_OK(c, c->GetAttr("precision", &precision_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor &x = ctx->input(0), &stat = ctx->input(1), &dy = ctx->input(2);
+    const NvaeConvDesc d = conv_desc(x.dim_size(0), x.dim_size(1), x.dim_size(2), x.dim_size(3), 0, dy.dim_size(3), 1, 1,
+                                     1, precision_);
+    Tensor *dw = nullptr, *db = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({1, 1, d.Cin, d.Cout}), &dw));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape({d.Cout}), &db));
+    Tensor ws;
+    const size_t ws_bytes = nvae_conv2d_ws_bytes(&d, 2);
+    OP_REQUIRES_OK(ctx, alloc_ws(ctx, ws_bytes, &ws));
+    const int rc = nvae_conv2d_wgrad_bnact(&d, fptr(x), fptr(stat), act_, fptr(dy), fptr(dw), fptr(db),
+                                           ws.flat<uint8>().data(), ws_bytes, stream_of(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("nvae_conv2d_wgrad_bnact failed: ", rc));
+  }
+ private:
+  int act_, precision_;
+};
+REGISTER_KERNEL_BUILDER(Name("NvaeConv2dWgradBnact").Device(DEVICE_GPU), NvaeConv2dWgradBnactOp);
+
+// ------------------------------------------------------------------------------------------------
 // BatchNormalization(momentum=0.05, epsilon=1e-5) + swish / ELU (+ nearest x2): common.py:148,165-172;
 // encoder.py:91-104; decoder.py:125-145.  moving_mean / moving_var are resource-style in/out buffers: the op updates
 // the tensors it is given in place (they are passed as ref-like inputs by the Python wrapper).

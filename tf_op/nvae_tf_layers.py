@@ -80,6 +80,29 @@ def dwconv_bn_act(x, bn, depthwise_kernel, bias, act=1, training=True):
     return f(x, bn.gamma, bn.beta, depthwise_kernel, bias)
 
 
+def bn_conv2d(x, bn, kernel, kernel_tr, bias, act=1, training=True, residual=None, precision=2):
+    """SpectralNormalization(Conv2D(1x1))(act(BN(x))) (+ residual) with the BN-apply + activation inside the convolution's
+    operand path, forward and backward-filter: decoder.py:125-127 (act=0), 143-144; postprocess.py:71-73 (act=0), 84-96.
+    For the shapes of those call sites; NvaeConv2dFwdBnact raises InvalidArgument for any other -- compose
+    conv2d(bn_act(x, ...), ...) there."""
+    res_ = _EMPTY if residual is None else residual
+
+    @tf.custom_gradient
+    def f(x, gamma, beta, kernel, bias, res_):
+        stat = bn_stat(x, bn, training)
+        y = _ops.nvae_conv2d_fwd_bnact(x=x, stat=stat, w=kernel, w_tr=kernel_tr, bias=bias, residual=res_, act=act,
+                                       precision=precision)
+
+        def grad(dy):
+            da, _ = _ops.nvae_conv2d_dgrad(dy=dy, w=kernel, w_rnd=kernel, in_h=x.shape[1], in_w=x.shape[2], cin=x.shape[3],
+                                           cin2=0, stride=1, precision=precision)
+            dw, db = _ops.nvae_conv2d_wgrad_bnact(x=x, stat=stat, dy=dy, act=act, precision=precision)
+            dx, dgamma, dbeta = _ops.nvae_bn_act_bwd(dout=da, x=x, stat=stat, training=training, act=act, upsample=False)
+            return dx, dgamma, dbeta, dw, db, (None if residual is None else dy)
+        return y, grad
+    return f(x, bn.gamma, bn.beta, kernel, bias, res_)
+
+
 def se_residual(t, xres, se, alpha=0.1, beta=1.0, bn=None, training=True):
     """alpha * xres + beta * SqueezeExcitation(BN(t)) (bn optional): common.py:129-142 with the cell tails encoder.py:107,
     decoder.py:147 (alpha=0.1, beta=1) and preprocess.py:107, postprocess.py:58 (alpha=1, beta=0.1)."""
